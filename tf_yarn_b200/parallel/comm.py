@@ -15,6 +15,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from tf_yarn_b200.ops import native
+from tf_yarn_b200.parallel.optspec import OptimizerSpec  # noqa: F401  (re-export)
 from tf_yarn_b200.parallel.symm import Rendezvous, SymmArena
 
 _DT = {torch.bfloat16: native.BF16, torch.float32: native.F32}
@@ -54,6 +55,10 @@ class Communicator:
     def pick_algo(self, nbytes: int) -> int:
         if self.world == 1 or nbytes <= ONESHOT_MAX_BYTES:
             return native.ALGO_ONESHOT
+        return native.ALGO_NVLS if self.multicast else native.ALGO_TWOSHOT
+
+    def pick_algo_inplace(self) -> int:
+        """Algorithm for in-place reduction of an arena buffer (one-shot needs a separate output)."""
         return native.ALGO_NVLS if self.multicast else native.ALGO_TWOSHOT
 
     def pad_elems(self, n: int, dtype: torch.dtype) -> int:
@@ -223,47 +228,6 @@ class Communicator:
 # ---------------------------------------------------------------------------
 # K4: fused reduce-scatter -> optimizer -> all-gather over flat buffers
 # ---------------------------------------------------------------------------
-class OptimizerSpec:
-    """Hyper-parameters of a fused optimizer (device-independent description)."""
-
-    KINDS = {"sgd": native.OPT_SGD, "adadelta": native.OPT_ADADELTA, "adam": native.OPT_ADAM,
-             "adamw": native.OPT_ADAM, "adagrad": native.OPT_ADAGRAD}
-
-    def __init__(self, kind: str, lr: float, p1: float = 0.0, p2: float = 0.0, eps: float = 1e-7,
-                 weight_decay: float = 0.0, flags: int = 0, init_s1: float = 0.0):
-        kind = kind.lower()
-        if kind not in self.KINDS:
-            raise ValueError(f"unknown fused optimizer {kind!r}")
-        self.kind, self.lr, self.p1, self.p2, self.eps = kind, float(lr), float(p1), float(p2), float(eps)
-        self.weight_decay, self.flags, self.init_s1 = float(weight_decay), int(flags), float(init_s1)
-        if kind == "adamw":
-            self.flags |= 1
-
-    @property
-    def code(self) -> int:
-        return self.KINDS[self.kind]
-
-    @property
-    def n_states(self) -> int:
-        return 2 if self.kind in ("adadelta", "adam", "adamw") else 1
-
-    @staticmethod
-    def sgd(lr, momentum=0.0, dampening=0.0, nesterov=False, weight_decay=0.0):
-        return OptimizerSpec("sgd", lr, momentum, dampening, 0.0, weight_decay, 1 if nesterov else 0)
-
-    @staticmethod
-    def adadelta(lr=1.0, rho=0.95, eps=1e-7, weight_decay=0.0):
-        return OptimizerSpec("adadelta", lr, rho, 0.0, eps, weight_decay)
-
-    @staticmethod
-    def adam(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, decoupled=False):
-        return OptimizerSpec("adamw" if decoupled else "adam", lr, beta1, beta2, eps, weight_decay)
-
-    @staticmethod
-    def adagrad(lr=1e-2, eps=1e-10, weight_decay=0.0, initial_accumulator_value=0.0):
-        return OptimizerSpec("adagrad", lr, 0.0, 0.0, eps, weight_decay, init_s1=initial_accumulator_value)
-
-
 class FusedShardedOptimizer:
     """Flat parameter / gradient buffers + the fused K4 step.
 
