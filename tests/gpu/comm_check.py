@@ -125,6 +125,8 @@ def main():
     ap.add_argument("--backend", default="vmm", choices=["vmm", "torch", "both"])
     args = ap.parse_args()
 
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("TFY_CHECK_DUMP_AFTER", "100")), exit=True)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -144,6 +146,7 @@ def main():
         tag = backend
         try:
             arena_bytes = ((1 << 30) if args.quick else (4 << 30)) + (64 << 20)
+            print(f"[rank {rank}] setting up {backend} arena", flush=True)
             if backend == "vmm":
                 store = dist.distributed_c10d._get_default_store()
                 rdv = StoreRendezvous(store, rank, world, prefix=f"chk_{backend}")
@@ -267,6 +270,14 @@ def main():
                     tol = 2e-2 if pdt == torch.bfloat16 else 2e-4
                     if gdt == torch.bfloat16 and comm.mode != native.MODE_NVLS:
                         tol = max(tol, 2e-2)
+                    # the replicated compute params must be exactly the (gathered) fp32 master cast down
+                    if rel >= tol and rank == 0:
+                        relv = (got - expect).abs() / denom
+                        worst_idx = torch.topk(relv, 8).indices
+                        print(f"[diag] {kind}/{pdt} step {step}: worst idx {worst_idx.tolist()} "
+                              f"got {got[worst_idx].tolist()} expect {expect[worst_idx].tolist()} "
+                              f"G {G[worst_idx].tolist()} n={fo.n} shard={fo.shard_n} "
+                              f"n_bad={(relv >= tol).sum().item()}", flush=True)
                     ok = ok and rel < tol and bool((fo.flat_grads == 0).all().item())
                 stp = fo.step_count
                 ok = ok and stp == 4
@@ -371,7 +382,7 @@ def main():
 
     if rank == 0:
         os.makedirs("gpurun_out", exist_ok=True)
-        with open(f"gpurun_out/comm_check_N{world}.json", "w") as f:
+        with open(f"gpurun_out/comm_check_N{world}_{args.backend}.json", "w") as f:
             json.dump(results, f, indent=1)
         n_fail = sum(1 for t in results["tests"].values() if not t["ok"]) + len(results["errors"])
         print(f"SUMMARY world={world} tests={len(results['tests'])} failed={n_fail}", flush=True)

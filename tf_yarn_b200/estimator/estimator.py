@@ -1,0 +1,448 @@
+"""``Estimator``: train / evaluate / predict driven by a ``model_fn``, checkpoints in ``model_dir``.
+
+Torch-backed stand-in for ``tf.estimator.Estimator`` with the attributes and
+methods the reference's task programs rely on (reference:
+tf_yarn/tensorflow/tasks/gloo_allred_task.py:58-75 -- ``estimator._model_dir`` /
+``estimator._config`` are assigned, ``estimator.train(input_fn, hooks, max_steps)``;
+tf_yarn/tensorflow/tasks/evaluator_task.py:103-121 -- ``estimator.evaluate(input_fn,
+steps, hooks, name, checkpoint_path)`` returning a dict holding the global step).
+
+Three training data planes, chosen from the process's role:
+
+* local / single process  -- plain optimizer step;
+* all-reduce (``optimizer`` wrapped by ``hvd.DistributedOptimizer``) -- gradients
+  averaged across ranks (fused K4 kernel on B200, gloo on CPU);
+* parameter server (``TF_CONFIG`` lists ``ps`` tasks) -- parameters live on the ps
+  ranks; workers pull before and push after every step, asynchronously
+  (:mod:`tf_yarn_b200.estimator.ps`).
+"""
+from __future__ import annotations
+
+import inspect
+import logging
+import os
+import tempfile
+import time
+from typing import Any, Callable, Dict, Iterable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from tf_yarn_b200.estimator import checkpoint as ckpt
+from tf_yarn_b200.estimator import summary as summary_lib
+from tf_yarn_b200.estimator.config import RunConfig
+from tf_yarn_b200.estimator.hooks import (GLOBAL_STEP, SessionRunArgs, SessionRunContext, SessionRunValues)
+from tf_yarn_b200.estimator.spec import EstimatorSpec, GraphKeys, ModeKeys
+from tf_yarn_b200.keras import optimizers as kopt
+
+logger = logging.getLogger(__name__)
+
+
+def _call_model_fn(model_fn: Callable, features, labels, mode, params, config) -> EstimatorSpec:
+    sig = inspect.signature(model_fn).parameters
+    kwargs = {}
+    if "labels" in sig:
+        kwargs["labels"] = labels
+    if "mode" in sig:
+        kwargs["mode"] = mode
+    if "params" in sig:
+        kwargs["params"] = params
+    if "config" in sig:
+        kwargs["config"] = config
+    return model_fn(features, **kwargs)
+
+
+def _to_device(t, device):
+    if t is None:
+        return None
+    if isinstance(t, dict):
+        return {k: _to_device(v, device) for k, v in t.items()}
+    if isinstance(t, (tuple, list)):
+        return type(t)(_to_device(v, device) for v in t)
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    if t.dtype == torch.float64:
+        t = t.float()
+    return t.to(device, non_blocking=True)
+
+
+def _split(item):
+    if isinstance(item, (tuple, list)) and len(item) == 2:
+        return item[0], item[1]
+    return item, None
+
+
+class Estimator:
+    def __init__(self, model_fn: Callable, model_dir: Optional[str] = None, config: Optional[RunConfig] = None,
+                 params: Optional[Dict[str, Any]] = None, warm_start_from: Optional[str] = None):
+        self._model_fn = model_fn
+        self._config = config or RunConfig()
+        self._model_dir = model_dir or self._config.model_dir or tempfile.mkdtemp(prefix="tfy_estimator_")
+        if self._config.model_dir is None:
+            self._config = self._config.replace(model_dir=self._model_dir)
+        self._params = dict(params or {})
+        self._warm_start_from = warm_start_from
+        self._network: Optional[nn.Module] = None
+        self._spec: Optional[EstimatorSpec] = None
+        self._optimizer = None
+        self._opt_desc: Optional[kopt.Optimizer] = None
+        self._global_step = 0
+        self._device: Optional[torch.device] = None
+        self._ps = None
+        self._pending_broadcast: Optional[int] = None
+        self.last_loss: Optional[float] = None
+
+    # -- properties the reference's tasks read / assign ---------------------------
+    @property
+    def model_dir(self) -> str:
+        return self._model_dir
+
+    @property
+    def config(self) -> RunConfig:
+        return self._config
+
+    @property
+    def params(self) -> Dict[str, Any]:
+        return self._params
+
+    @property
+    def model_fn(self) -> Callable:
+        return self._model_fn
+
+    def get_global_step(self) -> int:
+        return self._global_step
+
+    # ---------------------------------------------------------------------- build
+    def _default_device(self) -> torch.device:
+        if torch.cuda.is_available():
+            ids = [int(v) for v in os.environ.get("TFY_GPU_IDS", "").split(",") if v.strip() != ""]
+            return torch.device(f"cuda:{ids[0]}" if ids else f"cuda:{torch.cuda.current_device()}")
+        return torch.device("cpu")
+
+    def _build(self, features, labels, mode: str) -> EstimatorSpec:
+        spec = _call_model_fn(self._model_fn, features, labels, mode, self._params, self._config)
+        if not isinstance(spec, EstimatorSpec):
+            raise TypeError("model_fn must return an EstimatorSpec")
+        if self._network is None:
+            self._device = self._device or self._default_device()
+            self._network = spec.network.to(self._device) if spec.network is not None else None
+            if self._config.tf_random_seed is not None:
+                torch.manual_seed(self._config.tf_random_seed)
+        self._spec = spec._replace(network=self._network)
+        return self._spec
+
+    def _make_optimizer(self, spec: EstimatorSpec):
+        opt = spec.optimizer
+        if opt is None:
+            opt = "sgd"
+        if callable(opt) and not isinstance(opt, kopt.Optimizer) and not hasattr(opt, "_tfy_inner_optimizer"):
+            opt = opt()
+        desc = kopt.get(opt)
+        self._opt_desc = desc
+        params = [p for p in self._network.parameters() if p.requires_grad] if self._network is not None else []
+        self._optimizer = desc.to_torch(params) if params else None
+
+    def _variables(self) -> List[torch.Tensor]:
+        if self._network is None:
+            return []
+        return [p.data for p in self._network.parameters()] + [b.data for b in self._network.buffers()]
+
+    def broadcast_variables(self, root: int = 0) -> None:
+        if self._network is None:
+            self._pending_broadcast = root
+            return
+        from tf_yarn_b200 import hvd
+        if hvd.is_initialized() and hvd.size() > 1:
+            hvd.broadcast_parameters(self._variables(), root)
+
+    # ------------------------------------------------------------------ checkpoints
+    def latest_checkpoint(self) -> Optional[str]:
+        return ckpt.latest_checkpoint(self._model_dir)
+
+    def _save(self) -> str:
+        payload = {"global_step": self._global_step,
+                   "network": self._network.state_dict() if self._network is not None else None,
+                   "optimizer": self._optimizer.state_dict() if self._optimizer is not None else None}
+        if self._ps is not None:
+            payload["network"] = self._ps.state_dict_from_ps(self._network)
+        path = ckpt.save_checkpoint(self._model_dir, self._global_step, payload, self._config.keep_checkpoint_max)
+        logger.info("Saved checkpoint for step %d: %s", self._global_step, path)
+        return path
+
+    def _restore(self, path: Optional[str] = None, with_optimizer: bool = True) -> bool:
+        path = path or self.latest_checkpoint() or self._warm_start_from
+        if not path or not os.path.exists(path):
+            return False
+        payload = ckpt.load_checkpoint(path, map_location=self._device or "cpu")
+        if self._network is not None and payload.get("network") is not None:
+            self._network.load_state_dict(payload["network"])
+        if with_optimizer and self._optimizer is not None and payload.get("optimizer") is not None:
+            try:
+                self._optimizer.load_state_dict(payload["optimizer"])
+            except (ValueError, KeyError):
+                logger.warning("optimizer state in %s does not match; starting it fresh", path)
+        self._global_step = int(payload.get("global_step", 0))
+        logger.info("Restored from %s (global step %d)", path, self._global_step)
+        return True
+
+    # ------------------------------------------------------------------------ train
+    def train(self, input_fn: Callable, hooks: Optional[Iterable] = None, steps: Optional[int] = None,
+              max_steps: Optional[int] = None, saving_listeners=None) -> "Estimator":
+        """Run training steps until ``steps`` more were done, ``max_steps`` is reached, the input is
+        exhausted or a hook requests a stop."""
+        from tf_yarn_b200.estimator import ps as ps_mod
+        hooks = list(hooks or [])
+        cfg = self._config
+        cluster = cfg.cluster
+        dataset = input_fn()
+        it = iter(dataset)
+        first = next(it, None)
+        if first is None:
+            return self
+        features, labels = _split(first)
+        spec = self._build(features, labels, ModeKeys.TRAIN)
+        if self._optimizer is None and self._opt_desc is None:
+            self._make_optimizer(spec)
+        distributed = bool(self._opt_desc is not None and self._opt_desc.distributed)
+        if distributed:
+            from tf_yarn_b200 import hvd
+            if not hvd.is_initialized():
+                hvd.init()
+            if self._device.type != "cuda":
+                hvd.ensure_cpu_group()
+        is_chief = cluster.is_chief
+        use_ps = cluster.has_ps and cluster.task_type in ("chief", "worker")
+        self._restore()
+        if use_ps and self._ps is None and self._network is not None:
+            self._ps = ps_mod.connect_worker(self._network, self._opt_desc, cluster, is_chief, self._global_step)
+            if not is_chief:
+                self._global_step = self._ps.global_step()
+        if self._pending_broadcast is not None:
+            root, self._pending_broadcast = self._pending_broadcast, None
+            self.broadcast_variables(root)
+
+        writes_files = is_chief and cfg.model_dir is not None
+        writer = summary_lib.writer(self._model_dir) if (writes_files and cfg.save_summary_steps) else None
+        for h in hooks:
+            h.begin()
+        for h in hooks:
+            try:
+                h.after_create_session(self, None)
+            except TypeError:
+                h.after_create_session()
+        if writes_files and self._global_step == 0 and \
+                (cfg.save_checkpoints_steps or cfg.save_checkpoints_secs) and self.latest_checkpoint() is None:
+            self._save()
+
+        ctx = SessionRunContext(self, self._global_step)
+        start_step = self._global_step
+        last_save_time = time.time()
+        last_log_time, last_log_step = time.time(), self._global_step
+        item = first
+        if self._network is not None:
+            self._network.train()
+        while item is not None:
+            if max_steps is not None and self._global_step >= max_steps:
+                break
+            if steps is not None and self._global_step - start_step >= steps:
+                break
+            features, labels = _split(item)
+            wants_step = [h for h in hooks if _wants_global_step(h.before_run(ctx))]
+            loss = self._train_step(features, labels, distributed)
+            if self._ps is not None:
+                self._global_step = self._ps.increment_global_step()
+            else:
+                self._global_step += 1
+            ctx.step = self._global_step
+            for h in hooks:
+                h.after_run(ctx, SessionRunValues(results=self._global_step if h in wants_step else None))
+            gs = self._global_step
+            if writer is not None and cfg.save_summary_steps and gs % cfg.save_summary_steps == 0:
+                self.last_loss = float(loss)
+                writer.add_scalar("loss", self.last_loss, gs)
+            if cfg.log_step_count_steps and gs - last_log_step >= cfg.log_step_count_steps:
+                now = time.time()
+                self.last_loss = float(loss)
+                sps = (gs - last_log_step) / max(now - last_log_time, 1e-9)
+                logger.info("global_step/sec: %.4g  loss = %.6g, step = %d", sps, self.last_loss, gs)
+                if writer is not None:
+                    writer.add_scalar("global_step/sec", sps, gs)
+                last_log_time, last_log_step = now, gs
+            if writes_files:
+                due = (cfg.save_checkpoints_steps and gs % cfg.save_checkpoints_steps == 0) or \
+                      (cfg.save_checkpoints_secs and time.time() - last_save_time >= cfg.save_checkpoints_secs)
+                if due:
+                    self._save()
+                    last_save_time = time.time()
+            if ctx.stop_requested:
+                break
+            item = next(it, None)
+        self.last_loss = float(loss) if self._global_step > start_step else self.last_loss
+        if writes_files and (cfg.save_checkpoints_steps or cfg.save_checkpoints_secs) and \
+                self._global_step > start_step:
+            st = ckpt.get_checkpoint_state(self._model_dir)
+            if st is None or ckpt.step_of(st.model_checkpoint_path) != self._global_step:
+                self._save()
+        for h in hooks:
+            try:
+                h.end(None)
+            except TypeError:
+                h.end()
+        if writer is not None:
+            writer.flush()
+            writer.close()
+        logger.info("Loss for final step: %s.", self.last_loss)
+        return self
+
+    def _train_step(self, features, labels, distributed: bool) -> torch.Tensor:
+        spec = self._spec
+        if self._network is None or self._optimizer is None:
+            return torch.zeros(())
+        features = _to_device(features, self._device)
+        labels = _to_device(labels, self._device)
+        if self._ps is not None:
+            self._ps.pull(self._network)
+        self._optimizer.zero_grad(set_to_none=False)
+        outputs = self._network(features)
+        loss = spec.loss(labels, outputs)
+        loss.backward()
+        if self._ps is not None:
+            self._ps.push(self._network)
+            return loss.detach()
+        if distributed:
+            from tf_yarn_b200 import hvd
+            grads = [p.grad for p in self._network.parameters() if p.grad is not None]
+            hvd.grouped_allreduce_(grads, average=True)
+        self._optimizer.step()
+        return loss.detach()
+
+    # --------------------------------------------------------------------- evaluate
+    def evaluate(self, input_fn: Callable, steps: Optional[int] = None, hooks: Optional[Iterable] = None,
+                 checkpoint_path: Optional[str] = None, name: Optional[str] = None) -> Dict[str, Any]:
+        """Metrics over ``steps`` batches of ``input_fn()`` using ``checkpoint_path`` (default: latest).
+
+        Returns ``{"loss": ..., <metric>: ..., "global_step": step of the checkpoint}`` and writes the
+        same scalars to ``<model_dir>/eval[_<name>]`` as TensorBoard events.
+        """
+        hooks = list(hooks or [])
+        it = iter(input_fn())
+        first = next(it, None)
+        if first is None:
+            return {}
+        features, labels = _split(first)
+        spec = self._build(features, labels, ModeKeys.EVAL)
+        path = checkpoint_path or self.latest_checkpoint()
+        if path:
+            self._restore(path, with_optimizer=False)
+        elif self._ps is not None and self._network is not None:
+            self._ps.pull(self._network)
+        gs = self._global_step
+        for h in hooks:
+            h.begin()
+        for h in hooks:
+            try:
+                h.after_create_session(self, None)
+            except TypeError:
+                h.after_create_session()
+        ctx = SessionRunContext(self, gs)
+        metric_fns = dict(spec.eval_metric_ops or {})
+        num = {k: 0.0 for k in metric_fns}
+        den = {k: 0.0 for k in metric_fns}
+        loss_sum, n_batches = 0.0, 0
+        if self._network is not None:
+            self._network.eval()
+        item = first
+        with torch.no_grad():
+            while item is not None and (steps is None or n_batches < steps):
+                features, labels = _split(item)
+                wants_step = [h for h in hooks if _wants_global_step(h.before_run(ctx))]
+                features = _to_device(features, self._device or torch.device("cpu"))
+                labels = _to_device(labels, self._device or torch.device("cpu"))
+                outputs = self._network(features) if self._network is not None else features
+                if spec.loss is not None:
+                    loss_sum += float(spec.loss(labels, outputs))
+                for k, fn in metric_fns.items():
+                    a, b = fn(labels, outputs)
+                    num[k] += float(a)
+                    den[k] += float(b)
+                n_batches += 1
+                for h in hooks:
+                    h.after_run(ctx, SessionRunValues(results=gs if h in wants_step else None))
+                if ctx.stop_requested:
+                    break
+                item = next(it, None)
+        for h in hooks:
+            try:
+                h.end(None)
+            except TypeError:
+                h.end()
+        results: Dict[str, Any] = {"loss": loss_sum / max(n_batches, 1)}
+        for k in metric_fns:
+            results[k] = num[k] / max(den[k], 1.0)
+        results[GraphKeys.GLOBAL_STEP] = gs
+        eval_dir = os.path.join(self._model_dir, "eval" if not name else f"eval_{name}")
+        w = summary_lib.writer(eval_dir)
+        for k, v in results.items():
+            if k != GraphKeys.GLOBAL_STEP:
+                w.add_scalar(k, v, gs)
+        w.flush()
+        w.close()
+        logger.info("Saving dict for global step %d: %s", gs, results)
+        return results
+
+    # ---------------------------------------------------------------------- predict
+    def predict(self, input_fn: Callable, checkpoint_path: Optional[str] = None, yield_single_examples: bool = True):
+        it = iter(input_fn())
+        first = next(it, None)
+        if first is None:
+            return
+        features, _ = _split(first)
+        spec = self._build(features, None, ModeKeys.PREDICT)
+        path = checkpoint_path or self.latest_checkpoint()
+        if path:
+            self._restore(path, with_optimizer=False)
+        if self._network is not None:
+            self._network.eval()
+        item = first
+        with torch.no_grad():
+            while item is not None:
+                features, _ = _split(item)
+                features = _to_device(features, self._device or torch.device("cpu"))
+                outputs = self._network(features) if self._network is not None else features
+                preds = spec.predictions(outputs) if spec.predictions is not None else outputs
+                if yield_single_examples:
+                    if isinstance(preds, dict):
+                        n = next(iter(preds.values())).shape[0]
+                        for i in range(n):
+                            yield {k: v[i].cpu().numpy() for k, v in preds.items()}
+                    else:
+                        for row in preds:
+                            yield row.cpu().numpy() if torch.is_tensor(row) else row
+                else:
+                    yield preds
+                item = next(it, None)
+
+    # ----------------------------------------------------------------------- export
+    def export_saved_model(self, export_dir_base: str, serving_input_receiver_fn=None,
+                           checkpoint_path: Optional[str] = None, **_ignored) -> str:
+        """Write the network (weights of ``checkpoint_path``) under ``export_dir_base/<timestamp>``."""
+        path = checkpoint_path or self.latest_checkpoint()
+        if self._network is None:
+            raise RuntimeError("export needs a built network: call train() or evaluate() first")
+        if path:
+            self._restore(path, with_optimizer=False)
+        out = os.path.join(export_dir_base, str(int(time.time())))
+        os.makedirs(out, exist_ok=True)
+        tmp = os.path.join(out, f"saved_model.pt.tmp{os.getpid()}")
+        import cloudpickle
+        with open(tmp, "wb") as f:
+            cloudpickle.dump({"network": self._network.to("cpu"), "global_step": self._global_step}, f)
+        os.replace(tmp, os.path.join(out, "saved_model.pt"))
+        self._network.to(self._device)
+        return out
+
+    export_savedmodel = export_saved_model
+
+
+def _wants_global_step(args) -> bool:
+    return isinstance(args, SessionRunArgs) and args.fetches == GLOBAL_STEP

@@ -175,9 +175,9 @@ bool send_fd(const Symm* s, int dst, int tag, int fd) {
     memcpy(CMSG_DATA(cm), &fd, sizeof(int));
     ssize_t n = sendmsg(sock, &mh, 0);
     if (n != (ssize_t)sizeof(m)) { set_err("sendmsg: %s", strerror(errno)); close(sock); return false; }
-    // wait for the 1-byte ack so the fd is certainly installed in the peer before we close
-    char ack = 0;
-    if (recv(sock, &ack, 1, 0) != 1) { set_err("ack recv: %s", strerror(errno)); close(sock); return false; }
+    // No acknowledgement: the message (and the in-flight fd, which holds its own reference to the
+    // file) stays queued on the peer's not-yet-accepted connection after we close.  Waiting for an
+    // ack here would deadlock, because every rank sends to all peers before it starts accepting.
     close(sock);
     return true;
 }
@@ -203,8 +203,6 @@ bool recv_one(Symm* s, int timeout_ms) {
     int fd = -1;
     for (cmsghdr* cm = CMSG_FIRSTHDR(&mh); cm; cm = CMSG_NXTHDR(&mh, cm))
         if (cm->cmsg_level == SOL_SOCKET && cm->cmsg_type == SCM_RIGHTS) memcpy(&fd, CMSG_DATA(cm), sizeof(int));
-    char ack = 1;
-    (void)!send(conn, &ack, 1, 0);
     close(conn);
     if (fd < 0) { set_err("message without fd"); return false; }
     s->stash[{m.tag, m.src}] = fd;
@@ -240,6 +238,46 @@ bool map_handle(Symm* s, CUmemGenericAllocationHandle h, CUdeviceptr* va) {
 extern "C" {
 
 const char* tfy_symm_last_error() { return g_err; }
+
+// Host-only self test of the fd exchange (no CUDA): every rank publishes a memfd holding its rank
+// and must read back every peer's.  Run by tests/test_symm_fdx.py with several processes.
+int tfy_fdx_selftest(int rank, int world, const char* sock_prefix, int timeout_ms) {
+    Symm s;
+    s.rank = rank; s.world = world; s.sock_prefix = sock_prefix;
+    char name[64];
+    snprintf(name, sizeof(name), "/tmp/tfy_fdx_%d_%d", (int)getpid(), rank);
+    int fd = open(name, O_RDWR | O_CREAT | O_TRUNC, 0600);
+    if (fd < 0) { set_err("open: %s", strerror(errno)); return -1; }
+    unlink(name);
+    int32_t payload = 1000 + rank;
+    if (write(fd, &payload, 4) != 4) { set_err("write"); return -1; }
+    s.listen_fd = socket(AF_UNIX, SOCK_STREAM, 0);
+    sockaddr_un addr;
+    memset(&addr, 0, sizeof(addr));
+    addr.sun_family = AF_UNIX;
+    std::string p = sock_path(&s, rank);
+    unlink(p.c_str());
+    strncpy(addr.sun_path, p.c_str(), sizeof(addr.sun_path) - 1);
+    if (bind(s.listen_fd, (sockaddr*)&addr, sizeof(addr)) != 0 || listen(s.listen_fd, 4 * TFY_MAX_RANKS) != 0) {
+        set_err("bind/listen %s: %s", p.c_str(), strerror(errno));
+        return -1;
+    }
+    int rc = 0;
+    for (int r = 0; r < world && rc == 0; ++r)
+        if (r != rank && !send_fd(&s, r, TAG_MEM, fd)) rc = -1;
+    for (int r = 0; r < world && rc == 0; ++r) {
+        if (r == rank) continue;
+        int pfd = -1;
+        if (!take_fd(&s, TAG_MEM, r, &pfd, timeout_ms)) { rc = -1; break; }
+        int32_t got = 0;
+        if (pread(pfd, &got, 4, 0) != 4 || got != 1000 + r) { set_err("bad payload from %d: %d", r, got); rc = -2; }
+        close(pfd);
+    }
+    close(fd);
+    close(s.listen_fd);
+    unlink(p.c_str());
+    return rc;
+}
 
 // Step 1: allocate + map the local arena, export it, start listening.
 // Returns an opaque handle or nullptr.

@@ -138,10 +138,18 @@ class SymmArena:
             raise RuntimeError("tfy_symm_open: " + self.lib.tfy_symm_last_error().decode())
         tmo = int(timeout_s * 1000)
         self.multicast = False
+        dbg = os.environ.get("TFY_SYMM_DEBUG") == "1"
+
+        def trace(msg):
+            if dbg:
+                print(f"[symm rank {self.rank}] {msg}", flush=True)
+        trace("arena allocated, listening")
         if self.world > 1:
             self.rdv.barrier(f"{self._tag}/listening")
+            trace("exchanging memory handles")
             native.check(self.lib.tfy_symm_exchange(self._h, tmo), "tfy_symm_exchange")
             self.rdv.barrier(f"{self._tag}/exchanged")
+            trace("peers mapped; multicast setup")
             if os.environ.get("TFY_DISABLE_NVLS") == "1":
                 rc = 1
             else:
@@ -157,6 +165,7 @@ class SymmArena:
                 ok = all(self.rdv.get(f"{self._tag}/mcb/{r}") == b"0" for r in range(self.world))
                 self.multicast = bool(ok)
             self.rdv.barrier(f"{self._tag}/ready")
+            trace(f"ready, multicast={self.multicast}")
         self.size = int(self.lib.tfy_symm_size(self._h))
         self.peer_base = [int(self.lib.tfy_symm_peer_ptr(self._h, r)) for r in range(self.world)]
         self.mc_base = int(self.lib.tfy_symm_mc_ptr(self._h)) if self.multicast else 0
