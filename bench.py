@@ -43,58 +43,57 @@ METRIC = "samples/sec, Keras MNIST-CNN Horovod path (whole job)"
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clock + throttle reasons through NVML on a thread while the timed region runs
+    (10 ms period, so even a ~100 ms region gets ~10 samples; nvidia-smi -lms cannot go that fast)."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    REASONS = {
+        "hw_slowdown": 0x0000000000000008, "sw_power_cap": 0x0000000000000004,
+        "hw_thermal_slowdown": 0x0000000000000040, "sw_thermal_slowdown": 0x0000000000000020,
+        "hw_power_brake_slowdown": 0x0000000000000080,
+    }
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index: int, period_s: float = 0.01):
+        self.gpu, self.period = gpu_index, period_s
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
         self._t = None
+        self._h = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self._h = None
             return
-        self._t = threading.Thread(target=self._read, daemon=True)
+        self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()           # exactly the PID we started
-        try:
-            self.proc.wait(5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self._h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self._stop.set()
+        self._t.join(2)
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def _dist_env():

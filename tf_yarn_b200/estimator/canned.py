@@ -37,11 +37,11 @@ def _classification_metrics(n_classes: int) -> Dict[str, Callable]:
         else:
             pred = logits.argmax(dim=-1)
         labels = labels.long().reshape(-1)
-        return (pred == labels).sum().float(), torch.tensor(float(labels.numel()))
+        return (pred == labels).sum().float(), float(labels.numel())
 
     def average_loss(labels, logits):
         n = labels.reshape(-1).shape[0]
-        return _classification_loss(n_classes)(labels, logits) * n, torch.tensor(float(n))
+        return _classification_loss(n_classes)(labels, logits) * n, float(n)
     return {"accuracy": accuracy, "average_loss": average_loss}
 
 

@@ -1,4 +1,7 @@
-"""Streaming metrics: ``update(y_true, y_pred) -> (numerator, denominator)`` tensors on the device."""
+"""Streaming metrics: ``update(y_true, y_pred) -> (numerator, denominator)``.
+
+The numerator is a device tensor; the denominator (an element count) is a Python float so that
+no host->device copy happens inside a CUDA-graph capture."""
 from __future__ import annotations
 
 from typing import Callable, Tuple, Union
@@ -9,7 +12,7 @@ import torch
 def sparse_categorical_accuracy(y_true, y_pred) -> Tuple[torch.Tensor, torch.Tensor]:
     pred = y_pred.reshape(-1, y_pred.shape[-1]).argmax(dim=-1)
     y_true = y_true.long().reshape(-1)
-    return (pred == y_true).sum().float(), torch.tensor(float(y_true.numel()), device=y_pred.device)
+    return (pred == y_true).sum().float(), float(y_true.numel())
 
 
 def categorical_accuracy(y_true, y_pred):
@@ -19,12 +22,12 @@ def categorical_accuracy(y_true, y_pred):
 def binary_accuracy(y_true, y_pred):
     pred = (y_pred.float().reshape(-1) > 0.5)
     y_true = y_true.reshape(-1) > 0.5
-    return (pred == y_true).sum().float(), torch.tensor(float(y_true.numel()), device=y_pred.device)
+    return (pred == y_true).sum().float(), float(y_true.numel())
 
 
 def mean_absolute_error(y_true, y_pred):
     d = (y_pred.float() - y_true.float().reshape(y_pred.shape)).abs()
-    return d.sum(), torch.tensor(float(d.numel()), device=y_pred.device)
+    return d.sum(), float(d.numel())
 
 
 def resolve(identifier: Union[str, Callable], loss_name: str, output_dim: int) -> Tuple[str, Callable]:
