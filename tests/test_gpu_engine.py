@@ -1,0 +1,230 @@
+"""GPU tests of the B200 train engines (run with `pytest -m gpu` on a B200).
+
+Numerics of every hand-written kernel on the single-GPU path are compared with a plain
+PyTorch fp32 reference of the same op.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mnist_like(drop1=0.0, drop2=0.0):
+    from tf_yarn_b200 import keras
+    from tf_yarn_b200.keras import layers
+    m = keras.Sequential(name="mnist_cnn_test")
+    m.add(layers.Conv2D(32, (3, 3), activation="relu", input_shape=(28, 28, 1)))
+    m.add(layers.Conv2D(64, (3, 3), activation="relu"))
+    m.add(layers.MaxPooling2D(pool_size=(2, 2)))
+    m.add(layers.Dropout(drop1))
+    m.add(layers.Flatten())
+    m.add(layers.Dense(128, activation="relu"))
+    m.add(layers.Dropout(drop2))
+    m.add(layers.Dense(10))
+    return m
+
+
+def _native_loaded():
+    from tf_yarn_b200.ops import native
+    assert native.load() is not None
+
+
+def test_native_library_loads():
+    _native_loaded()
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adadelta", "adam", "adagrad"])
+def test_fused_step_local_matches_torch_optim(kind):
+    """K4 in LOCAL mode (world=1) against torch.optim on fp32 tensors."""
+    from tf_yarn_b200.keras.engine import _solo_communicator
+    from tf_yarn_b200.parallel.comm import FusedShardedOptimizer, OptimizerSpec
+    comm = _solo_communicator(0)
+    shapes = [(33, 17), (129,), (64, 32, 3, 3)]
+    spec = {"sgd": OptimizerSpec.sgd(0.05, momentum=0.9, nesterov=True),
+            "adadelta": OptimizerSpec.adadelta(1.0, 0.95, 1e-7),
+            "adam": OptimizerSpec.adam(1e-3, weight_decay=0.01),
+            "adagrad": OptimizerSpec.adagrad(0.05, 1e-10, 0.0, 0.1)}[kind]
+    fo = FusedShardedOptimizer(comm, shapes, spec, param_dtype=torch.float32, grad_dtype=torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    init = [torch.randn(s, device="cuda", generator=g) * 0.3 for s in shapes]
+    fo.init_from(init, broadcast_root=None)
+    ref = [t.clone().requires_grad_(True) for t in init]
+    opt = {"sgd": lambda: torch.optim.SGD(ref, lr=0.05, momentum=0.9, nesterov=True),
+           "adadelta": lambda: torch.optim.Adadelta(ref, lr=1.0, rho=0.95, eps=1e-7),
+           "adam": lambda: torch.optim.Adam(ref, lr=1e-3, weight_decay=0.01),
+           "adagrad": lambda: torch.optim.Adagrad(ref, lr=0.05, eps=1e-10, initial_accumulator_value=0.1)}[kind]()
+    for step in range(5):
+        grads = [torch.randn(s, device="cuda", generator=g) * 0.5 for s in shapes]
+        for gv, gr, r in zip(fo.grad_views, grads, ref):
+            gv.copy_(gr)
+            r.grad = gr.clone()
+        fo.step()
+        opt.step()
+        torch.cuda.synchronize()
+        for pv, r in zip(fo.param_views, ref):
+            torch.testing.assert_close(pv, r.detach(), rtol=2e-5, atol=2e-6)
+        assert all(float(gv.abs().max()) == 0.0 for gv in fo.grad_views), "gradients must be zeroed by the step"
+    assert fo.step_count == 5
+
+
+def test_nn_kernels_match_torch():
+    """bias+relu+pool(+dropout off), its backward, act/bias backward, conv C_in=1 fwd/wgrad, xent head."""
+    import ctypes
+    import torch.nn.functional as F
+    from tf_yarn_b200.keras import fastpath  # noqa: F401  (declares the argtypes)
+    from tf_yarn_b200.ops import native
+    lib = native.load()
+    s = torch.cuda.current_stream().cuda_stream
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(5)
+    B, H, W, C = 16, 24, 24, 64
+    partial = torch.zeros(592 * 9 * 64, device=dev)
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    z = (torch.randn(B, H, W, C, device=dev, generator=g)).bfloat16()
+    bias = (torch.randn(C, device=dev, generator=g) * 0.1).bfloat16()
+    p = torch.empty(B, H // 2, W // 2, C, dtype=torch.bfloat16, device=dev)
+    code = torch.empty(B, H // 2, W // 2, C, dtype=torch.uint8, device=dev)
+    assert lib.tfy_bias_relu_pool_drop_fwd(z.data_ptr(), bias.data_ptr(), p.data_ptr(), code.data_ptr(), B, H, W, C,
+                                           0.0, 1, None, s) == 0
+    zr = (z.float() + bias.float()).permute(0, 3, 1, 2).requires_grad_(True)
+    pr = F.max_pool2d(F.relu(zr), 2)
+    torch.testing.assert_close(p.float(), pr.permute(0, 2, 3, 1).detach(), rtol=1e-2, atol=1e-2)
+    dp = (torch.randn(B, H // 2, W // 2, C, device=dev, generator=g)).bfloat16()
+    dz = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dev)
+    dbias = torch.empty(C, dtype=torch.bfloat16, device=dev)
+    assert lib.tfy_pool_drop_relu_bwd(dp.data_ptr(), code.data_ptr(), dz.data_ptr(), 1.0, B, H, W, C,
+                                      partial.data_ptr(), dbias.data_ptr(), counter.data_ptr(), s) == 0
+    pr.backward(dp.float().permute(0, 3, 1, 2))
+    torch.testing.assert_close(dz.float(), zr.grad.permute(0, 2, 3, 1), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(dbias.float(), zr.grad.sum((0, 2, 3)), rtol=2e-2, atol=5e-2)
+    assert int(counter.item()) == 0
+
+    # bias + relu (+ mask) forward, gated backward + bias gradient
+    rows, Cd = 128, 128
+    zd = torch.randn(rows, Cd, device=dev, generator=g).bfloat16()
+    bd = (torch.randn(Cd, device=dev, generator=g) * 0.1).bfloat16()
+    y = torch.empty_like(zd)
+    mask = torch.empty(rows, Cd, dtype=torch.uint8, device=dev)
+    assert lib.tfy_bias_act_drop_fwd(zd.data_ptr(), bd.data_ptr(), y.data_ptr(), mask.data_ptr(), rows, Cd, 1, 0.0, 7,
+                                     None, s) == 0
+    yr = F.relu(zd.float() + bd.float())
+    torch.testing.assert_close(y.float(), yr, rtol=1e-2, atol=1e-2)
+    dy = torch.randn(rows, Cd, device=dev, generator=g).bfloat16()
+    dzz = torch.empty_like(dy)
+    db = torch.empty(Cd, dtype=torch.bfloat16, device=dev)
+    assert lib.tfy_act_drop_bwd_bias(dy.data_ptr(), mask.data_ptr(), None, dzz.data_ptr(), 1.0, rows, Cd,
+                                     partial.data_ptr(), db.data_ptr(), counter.data_ptr(), s) == 0
+    ref = dy.float() * (yr > 0)
+    torch.testing.assert_close(dzz.float(), ref, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(db.float(), ref.sum(0), rtol=2e-2, atol=5e-2)
+    # dropout: keep fraction and scaling
+    yd = torch.empty_like(zd)
+    assert lib.tfy_bias_act_drop_fwd(zd.data_ptr(), None, yd.data_ptr(), mask.data_ptr(), rows, Cd, 0, 0.5, 11,
+                                     None, s) == 0
+    kept = (yd != 0).float().mean().item()
+    assert 0.45 < kept < 0.55, kept
+    nz = yd != 0
+    torch.testing.assert_close(yd.float()[nz], (zd.float() * 2)[nz], rtol=1e-2, atol=1e-2)
+
+    # conv 3x3 C_in=1 forward + weight gradient
+    Bc, Hc, Wc, O = 8, 28, 28, 32
+    x = torch.rand(Bc, Hc, Wc, 1, device=dev, generator=g)
+    w = (torch.randn(O, 3, 3, 1, device=dev, generator=g) * 0.3).bfloat16()
+    bc = (torch.randn(O, device=dev, generator=g) * 0.1).bfloat16()
+    yc = torch.empty(Bc, Hc - 2, Wc - 2, O, dtype=torch.bfloat16, device=dev)
+    assert lib.tfy_conv3x3_c1_fwd(x.data_ptr(), 1, w.data_ptr(), bc.data_ptr(), yc.data_ptr(), Bc, Hc, Wc, O, s) == 0
+    wr = w.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)      # [O, 1, 3, 3]
+    ycr = F.relu(F.conv2d(x.permute(0, 3, 1, 2), wr, bc.float()))
+    torch.testing.assert_close(yc.float(), ycr.permute(0, 2, 3, 1).detach(), rtol=1e-2, atol=1e-2)
+    dzc = torch.randn(Bc, Hc - 2, Wc - 2, O, device=dev, generator=g).bfloat16()
+    dw = torch.empty(O, 9, dtype=torch.bfloat16, device=dev)
+    assert lib.tfy_conv3x3_c1_wgrad(x.data_ptr(), 1, dzc.data_ptr(), partial.data_ptr(), dw.data_ptr(),
+                                    counter.data_ptr(), Bc, Hc, Wc, O, s) == 0
+    pre = F.conv2d(x.permute(0, 3, 1, 2), wr)
+    pre.backward(dzc.float().permute(0, 3, 1, 2))
+    torch.testing.assert_close(dw.float().view(O, 3, 3), wr.grad[:, 0], rtol=2e-2, atol=0.3)
+
+    # softmax cross-entropy head
+    Bx, Cx = 128, 10
+    lg = torch.randn(Bx, Cx, device=dev, generator=g).bfloat16()
+    bx = (torch.randn(Cx, device=dev, generator=g) * 0.1).bfloat16()
+    lab = torch.randint(0, Cx, (Bx,), device=dev, generator=g)
+    loss = torch.zeros((), device=dev)
+    dl = torch.empty(Bx, Cx, dtype=torch.bfloat16, device=dev)
+    dbx = torch.empty(Cx, dtype=torch.bfloat16, device=dev)
+    stats = torch.zeros(2, device=dev)
+    assert lib.tfy_softmax_xent(lg.data_ptr(), bx.data_ptr(), lab.data_ptr(), loss.data_ptr(), dl.data_ptr(),
+                                dbx.data_ptr(), stats.data_ptr(), Bx, Cx, s) == 0
+    lr_ = (lg.float() + bx.float()).requires_grad_(True)
+    lref = F.cross_entropy(lr_, lab)
+    lref.backward()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - lref.item()) < 1e-3
+    torch.testing.assert_close(dl.float(), lr_.grad, rtol=2e-2, atol=1e-4)
+    torch.testing.assert_close(dbx.float(), lr_.grad.sum(0), rtol=2e-2, atol=1e-3)
+    assert stats[1].item() == Bx and stats[0].item() == (lr_.argmax(1) == lab).sum().item()
+
+
+def _run_steps(fast: bool, steps: int = 4):
+    from tf_yarn_b200 import keras
+    torch.manual_seed(7)
+    m = _mnist_like(0.0, 0.0)
+    m.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True),
+              optimizer=keras.optimizers.Adadelta(1.0), metrics=["accuracy"], use_fast_path=fast)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(128 * steps, 28, 28, 1, generator=g)
+    y = torch.randint(0, 10, (128 * steps,), generator=g)
+    losses = []
+
+    class Rec(keras.callbacks.Callback):
+        needs_batch_logs = True
+
+        def on_train_batch_end(self, batch, logs=None):
+            losses.append(logs["loss"])
+    m.fit(x, y, batch_size=128, epochs=1, shuffle=False, verbose=0, callbacks=[Rec()])
+    return m, losses
+
+
+def test_fastpath_matches_autograd_engine():
+    """Same init, same batches, dropout off: the fused-kernel plan must track the autograd engine."""
+    from tf_yarn_b200.keras.fastpath import FastSequentialEngine
+    m_fast, l_fast = _run_steps(True)
+    m_ref, l_ref = _run_steps(False)
+    assert isinstance(m_fast._engine, FastSequentialEngine)
+    assert not isinstance(m_ref._engine, FastSequentialEngine)
+    assert len(l_fast) == len(l_ref) == 4
+    for a, b in zip(l_fast, l_ref):
+        assert math.isfinite(a) and abs(a - b) < 0.03 * max(1.0, abs(b)), (l_fast, l_ref)
+    wf, wr = m_fast.get_weights(), m_ref.get_weights()
+    for a, b in zip(wf, wr):
+        a, b = torch.as_tensor(a), torch.as_tensor(b)
+        denom = b.abs().max().clamp_min(1e-3)
+        assert ((a - b).abs().max() / denom) < 0.08, ((a - b).abs().max(), denom)
+    assert m_fast._engine.kernel_launches > 0
+
+
+def test_fit_learns_and_checkpoints(tmp_path):
+    from tf_yarn_b200 import keras
+    torch.manual_seed(0)
+    m = _mnist_like(0.25, 0.5)
+    m.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True),
+              optimizer=keras.optimizers.Adadelta(1.0), metrics=["accuracy"])
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(1024, 28, 28, 1, generator=g)
+    y = (x[:, :14, :14, 0].mean((1, 2)) > x[:, 14:, 14:, 0].mean((1, 2))).long()
+    h = m.fit(x, y, batch_size=128, epochs=6, shuffle=True, verbose=0)
+    assert h.history["loss"][-1] < h.history["loss"][0]
+    assert h.history["accuracy"][-1] > 0.7, h.history
+    path = str(tmp_path / "m.ckpt")
+    m.save(path)
+    m2 = keras.models.load_model(path)
+    acc = m2.evaluate(x, y, batch_size=256, return_dict=True)["accuracy"]
+    assert acc > 0.7
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()

@@ -1,0 +1,320 @@
+"""Fast path of the B200 train engine: explicit forward/backward out of fused kernels.
+
+For ``Sequential`` models made of Conv2D(3x3, valid, stride 1) / MaxPooling2D(2x2) /
+Dropout / Flatten / Dense layers with relu|linear activations and a sparse-categorical
+cross-entropy (from logits) head -- the MNIST-CNN of the headline benchmark, the wine MLP --
+the step does not go through autograd at all.  GEMM-shaped work goes to cuDNN / cuBLAS
+(library GEMMs) or to the hand-written kernels, and everything around it is fused
+(:mod:`ops/csrc/tfy_nn.cu`): bias+ReLU(+2x2 max-pool)(+dropout) in one kernel, backward
+gating + bias-gradient reduction in one kernel, the whole softmax/CE head in one kernel,
+weight gradients written straight into the flat gradient buffer consumed by the fused
+reduce-scatter/optimizer/all-gather kernel (no ``grad += g`` accumulation launches).
+
+22 launches per step instead of 53 (profiles/launches_*.csv).  Models outside this grammar
+use the autograd engine (:class:`GraphTrainEngine`).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from tf_yarn_b200.keras import layers as L
+from tf_yarn_b200.keras.engine import GraphTrainEngine
+from tf_yarn_b200.ops import native
+
+_vp, _i, _sz, _f, _u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_uint32
+native.declare("tfy_conv3x3_c1_fwd", [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
+native.declare("tfy_conv3x3_c1_wgrad", [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
+native.declare("tfy_bias_act_drop_fwd", [_vp, _vp, _vp, _vp, _sz, _i, _i, _f, _u32, _vp, _vp])
+native.declare("tfy_act_drop_bwd_bias", [_vp, _vp, _vp, _vp, _f, _sz, _i, _vp, _vp, _vp, _vp])
+native.declare("tfy_bias_relu_pool_drop_fwd", [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u32, _vp, _vp])
+native.declare("tfy_pool_drop_relu_bwd", [_vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp])
+native.declare("tfy_softmax_xent", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp])
+
+PARTIAL_BLOCKS = 592
+
+
+class _Stage:
+    """One fused stage of the plan."""
+
+    def __init__(self, kind: str, **kw):
+        self.kind = kind
+        self.__dict__.update(kw)
+
+
+def build_plan(model) -> Optional[List[_Stage]]:
+    """Pattern-match the layer list; None if the model is outside the fast-path grammar."""
+    from tf_yarn_b200.keras import losses as kl
+    loss = model.loss
+    if not (isinstance(loss, kl.SparseCategoricalCrossentropy) and loss.from_logits):
+        return None
+    for m in model._metrics_spec:
+        if m not in ("accuracy", "acc", "sparse_categorical_accuracy"):
+            return None
+    layers = [ly for ly in model.layers if not isinstance(ly, L.InputLayer)]
+    plan: List[_Stage] = []
+    i, n = 0, len(layers)
+    seen_flatten = False
+    while i < n:
+        ly = layers[i]
+        if isinstance(ly, L.Conv2D) and not seen_flatten:
+            if ly.kernel_size != (3, 3) or ly.strides != (1, 1) or ly.padding != "valid" or not ly.use_bias \
+                    or ly.activation_name not in ("relu", "linear") or ly.filters % 8:
+                return None
+            st = _Stage("conv", layer=ly, relu=ly.activation_name == "relu", pool=False, drop=0.0)
+            j = i + 1
+            if j < n and isinstance(layers[j], L.MaxPooling2D):
+                mp = layers[j]
+                h, w, _ = ly.output_shape_
+                if mp.pool_size != (2, 2) or mp.strides != (2, 2) or mp.padding != "valid" or not st.relu \
+                        or h % 2 or w % 2:
+                    return None
+                st.pool = True
+                j += 1
+            if j < n and isinstance(layers[j], L.Dropout):
+                st.drop = layers[j].rate
+                j += 1
+            plan.append(st)
+            i = j
+        elif isinstance(ly, L.Flatten):
+            seen_flatten = True
+            plan.append(_Stage("flatten"))
+            i += 1
+        elif isinstance(ly, L.Dense):
+            if not ly.use_bias or ly.activation_name not in ("relu", "linear"):
+                return None
+            last = all(isinstance(x, L.Dropout) for x in layers[i + 1:]) and i + 1 >= n
+            if last:
+                if ly.activation_name != "linear":
+                    return None
+                plan.append(_Stage("head", layer=ly))
+                i += 1
+            else:
+                if ly.units % 8 or ly.input_shape_[-1] % 8:
+                    return None
+                st = _Stage("dense", layer=ly, relu=ly.activation_name == "relu", drop=0.0)
+                j = i + 1
+                if j < n and isinstance(layers[j], L.Dropout):
+                    st.drop = layers[j].rate
+                    j += 1
+                plan.append(st)
+                i = j
+        else:
+            return None
+    if not plan or plan[-1].kind != "head":
+        return None
+    kinds = [s.kind for s in plan]
+    if "conv" in kinds and "flatten" not in kinds:
+        return None
+    if len(model.layers[0].input_shape_ or ()) not in (1, 3):
+        return None
+    return plan
+
+
+class FastSequentialEngine(GraphTrainEngine):
+    """GraphTrainEngine whose step body is the explicit fused-kernel plan."""
+
+    def __init__(self, model, plan: List[_Stage], *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.plan = plan
+        self.lib = native.load()
+        dev = self.device
+        width = 8
+        for st in plan:
+            if st.kind == "conv":
+                width = max(width, st.layer.filters, 9 * st.layer.filters)
+            elif st.kind == "dense":
+                width = max(width, st.layer.units)
+        self._partial = torch.zeros(PARTIAL_BLOCKS * width, dtype=torch.float32, device=dev)
+        self._counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._stats = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._seed = int(torch.initial_seed() & 0x7fffffff)
+        self._hp = self.fused.hyper.data_ptr()
+        self._k = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _s(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: {rc}")
+        self._k += 1
+
+    def _wb(self, layer):
+        mod = layer.module
+        return mod.weight, mod.bias
+
+    def pop_metrics(self):
+        self.stream.synchronize()
+        st = self._stats.cpu()
+        self._stats.zero_()
+        if not self.metric_fns:
+            return {}
+        return {self.metric_fns[0][0]: float(st[0] / st[1].clamp_min(1))}
+
+    def _capture(self, x, y) -> None:
+        super()._capture(x, y)
+        with torch.cuda.stream(self.stream):
+            self._stats.zero_()          # warm-up steps must not count in the epoch metrics
+        self.stream.synchronize()
+
+    # ------------------------------------------------------------------ the step
+    def _forward_backward(self, x, y) -> None:
+        lib, s = self.lib, self._s()
+        self._k = 0
+        B = x.shape[0]
+        bf16 = torch.bfloat16
+        saved = []
+        cur = x                    # NHWC for images, [B, F] for vectors
+        cur_is_f32 = cur.dtype == torch.float32
+        # -------- forward
+        for li, st in enumerate(self.plan):
+            seed = (self._seed * 2654435761 + li * 97) & 0x7fffffff
+            if st.kind == "conv":
+                ly = st.layer
+                w, b = self._wb(ly)
+                H, W, Cin = ly.input_shape_
+                O = ly.filters
+                OH, OW = H - 2, W - 2
+                fused_pre = False
+                if Cin == 1:
+                    # direct kernel: conv + bias + relu in one launch (relu folded only when requested)
+                    a = torch.empty((B, OH, OW, O), dtype=bf16, device=cur.device)
+                    if st.relu and not st.pool:
+                        self._chk(lib.tfy_conv3x3_c1_fwd(cur.data_ptr(), int(cur_is_f32), w.data_ptr(), b.data_ptr(),
+                                                         a.data_ptr(), B, H, W, O, s), "conv3x3_c1_fwd")
+                        fused_pre = True
+                        z = a
+                    else:
+                        z = None
+                else:
+                    z = None
+                if z is None:
+                    xin = cur.to(bf16) if cur.dtype != bf16 else cur
+                    zc = F.conv2d(xin.permute(0, 3, 1, 2), w)       # NCHW logical over NHWC bytes
+                    z = zc.permute(0, 2, 3, 1)
+                    if not z.is_contiguous():
+                        z = z.contiguous()
+                if st.pool:
+                    p = torch.empty((B, OH // 2, OW // 2, O), dtype=bf16, device=cur.device)
+                    code = torch.empty((B, OH // 2, OW // 2, O), dtype=torch.uint8, device=cur.device)
+                    self._chk(lib.tfy_bias_relu_pool_drop_fwd(z.data_ptr(), b.data_ptr(), p.data_ptr(), code.data_ptr(),
+                                                              B, OH, OW, O, float(st.drop), seed, self._hp, s),
+                              "bias_relu_pool_drop_fwd")
+                    saved.append((cur, cur_is_f32, None, code))
+                    cur = p
+                else:
+                    mask = None
+                    if not fused_pre:
+                        if st.drop > 0:
+                            mask = torch.empty((B, OH, OW, O), dtype=torch.uint8, device=cur.device)
+                        self._chk(lib.tfy_bias_act_drop_fwd(z.data_ptr(), b.data_ptr(), z.data_ptr(),
+                                                            mask.data_ptr() if mask is not None else None,
+                                                            B * OH * OW, O, int(st.relu), float(st.drop), seed,
+                                                            self._hp, s), "bias_act_drop_fwd")
+                    elif st.drop > 0:
+                        mask = torch.empty((B, OH, OW, O), dtype=torch.uint8, device=cur.device)
+                        self._chk(lib.tfy_bias_act_drop_fwd(z.data_ptr(), None, z.data_ptr(), mask.data_ptr(),
+                                                            B * OH * OW, O, 1, float(st.drop), seed, self._hp, s),
+                                  "bias_act_drop_fwd")
+                    saved.append((cur, cur_is_f32, z, mask))
+                    cur = z
+                cur_is_f32 = False
+            elif st.kind == "flatten":
+                saved.append(cur.shape)
+                cur = cur.reshape(B, -1)
+            elif st.kind == "dense":
+                ly = st.layer
+                w, b = self._wb(ly)
+                xin = cur.to(bf16) if cur.dtype != bf16 else cur
+                z = torch.mm(xin, w.t())
+                mask = torch.empty((B, ly.units), dtype=torch.uint8, device=cur.device) \
+                    if (st.drop > 0 or st.relu) else None
+                self._chk(lib.tfy_bias_act_drop_fwd(z.data_ptr(), b.data_ptr(), z.data_ptr(),
+                                                    mask.data_ptr() if mask is not None else None, B, ly.units,
+                                                    int(st.relu), float(st.drop), seed, self._hp, s),
+                          "bias_act_drop_fwd")
+                saved.append((xin, mask))
+                cur = z
+                cur_is_f32 = False
+            else:  # head
+                ly = st.layer
+                w, b = self._wb(ly)
+                xin = cur.to(bf16) if cur.dtype != bf16 else cur
+                logits = torch.mm(xin, w.t())
+                C = ly.units
+                dlogits = torch.empty((B, C), dtype=bf16, device=cur.device)
+                self._chk(lib.tfy_softmax_xent(logits.data_ptr(), b.data_ptr(), y.data_ptr(), self._loss.data_ptr(),
+                                               dlogits.data_ptr(), b.grad.data_ptr(),
+                                               self._stats.data_ptr() if self.metric_fns else None, B, C, s),
+                          "softmax_xent")
+                saved.append((xin, dlogits))
+        # -------- backward
+        grad = None
+        for li in range(len(self.plan) - 1, -1, -1):
+            st = self.plan[li]
+            sv = saved[li]
+            first = li == 0
+            if st.kind == "head":
+                xin, dlogits = sv
+                w, _ = self._wb(st.layer)
+                torch.mm(dlogits.t(), xin, out=w.grad)
+                grad = torch.mm(dlogits, w) if not first else None
+            elif st.kind == "dense":
+                xin, mask = sv
+                ly = st.layer
+                w, b = self._wb(ly)
+                scale = 1.0 / (1.0 - st.drop) if st.drop > 0 else 1.0
+                self._chk(lib.tfy_act_drop_bwd_bias(grad.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                                    None, grad.data_ptr(), scale, B, ly.units,
+                                                    self._partial.data_ptr(), b.grad.data_ptr(),
+                                                    self._counter.data_ptr(), s), "act_drop_bwd_bias")
+                torch.mm(grad.t(), xin, out=w.grad)
+                grad = torch.mm(grad, w) if not first else None
+            elif st.kind == "flatten":
+                if grad is not None:
+                    grad = grad.reshape(sv)
+            else:  # conv
+                xin, xin_f32, zout, aux = sv
+                ly = st.layer
+                w, b = self._wb(ly)
+                H, W, Cin = ly.input_shape_
+                O = ly.filters
+                OH, OW = H - 2, W - 2
+                scale = 1.0 / (1.0 - st.drop) if st.drop > 0 else 1.0
+                if st.pool:
+                    dz = torch.empty((B, OH, OW, O), dtype=bf16, device=grad.device)
+                    self._chk(lib.tfy_pool_drop_relu_bwd(grad.data_ptr(), aux.data_ptr(), dz.data_ptr(), scale, B, OH,
+                                                         OW, O, self._partial.data_ptr(), b.grad.data_ptr(),
+                                                         self._counter.data_ptr(), s), "pool_drop_relu_bwd")
+                else:
+                    dz = grad if grad.is_contiguous() else grad.contiguous()
+                    use_mask = aux is not None
+                    self._chk(lib.tfy_act_drop_bwd_bias(dz.data_ptr(), aux.data_ptr() if use_mask else None,
+                                                        zout.data_ptr() if (st.relu and not use_mask) else None,
+                                                        dz.data_ptr(), scale, B * OH * OW, O,
+                                                        self._partial.data_ptr(), b.grad.data_ptr(),
+                                                        self._counter.data_ptr(), s), "act_drop_bwd_bias")
+                if Cin == 1:
+                    self._chk(lib.tfy_conv3x3_c1_wgrad(xin.data_ptr(), int(xin_f32), dz.data_ptr(),
+                                                       self._partial.data_ptr(), w.grad.data_ptr(),
+                                                       self._counter.data_ptr(), B, H, W, O, s), "conv3x3_c1_wgrad")
+                    grad = None
+                    if not first:
+                        raise RuntimeError("C_in=1 convolution must be the first layer")
+                else:
+                    xb = xin.to(bf16) if xin.dtype != bf16 else xin
+                    dx, dw, _ = torch.ops.aten.convolution_backward(
+                        dz.permute(0, 3, 1, 2), xb.permute(0, 3, 1, 2), w, None, [1, 1], [0, 0], [1, 1], False,
+                        [0, 0], 1, [not first, True, False])
+                    w.grad.copy_(dw)
+                    grad = None
+                    if not first:
+                        g = dx.permute(0, 2, 3, 1)
+                        grad = g if g.is_contiguous() else g.contiguous()
+        self.fused.step()
+        self._launches_per_step = self._k + 1     # our kernels launched per step (library GEMMs excluded)

@@ -136,6 +136,7 @@ class Model:
         self._device: Optional[torch.device] = None
         self.compute_dtype = torch.bfloat16
         self.use_cuda_graph = True
+        self.use_fast_path = True
         self.history = None
         self._pending_broadcast_root: Optional[int] = None
         for layer in layers or []:
@@ -191,7 +192,8 @@ class Model:
 
     # ------------------------------------------------------------------ compile
     def compile(self, optimizer="sgd", loss=None, metrics: Optional[Sequence[Any]] = None,
-                compute_dtype: Optional[torch.dtype] = None, use_cuda_graph: bool = True, **_ignored) -> None:
+                compute_dtype: Optional[torch.dtype] = None, use_cuda_graph: bool = True,
+                use_fast_path: bool = True, **_ignored) -> None:
         self.optimizer = opt_mod.get(optimizer)
         self.loss = loss
         self._loss_fn = loss_mod.get(loss) if loss is not None else None
@@ -199,6 +201,7 @@ class Model:
         if compute_dtype is not None:
             self.compute_dtype = compute_dtype
         self.use_cuda_graph = use_cuda_graph
+        self.use_fast_path = use_fast_path
         self._engine = None
 
     def _metric_fns(self) -> List[Tuple[str, Callable]]:
@@ -216,9 +219,18 @@ class Model:
         self.net.to(self._device)
         distributed = bool(self.optimizer.distributed)
         if self._device.type == "cuda":
-            self._engine = GraphTrainEngine(self.net, self._loss_fn, self.optimizer, self._metric_fns(),
-                                            self._device, distributed, x0, y0, self.compute_dtype,
-                                            self.use_cuda_graph)
+            plan = None
+            if self.use_fast_path and self.compute_dtype == torch.bfloat16:
+                from tf_yarn_b200.keras import fastpath
+                plan = fastpath.build_plan(self)
+            if plan is not None:
+                self._engine = fastpath.FastSequentialEngine(
+                    self, plan, self.net, self._loss_fn, self.optimizer, self._metric_fns(), self._device,
+                    distributed, x0, y0, self.compute_dtype, self.use_cuda_graph)
+            else:
+                self._engine = GraphTrainEngine(self.net, self._loss_fn, self.optimizer, self._metric_fns(),
+                                                self._device, distributed, x0, y0, self.compute_dtype,
+                                                self.use_cuda_graph)
         else:
             if distributed:
                 from tf_yarn_b200 import hvd

@@ -1,0 +1,483 @@
+// Fused layer kernels of the mini-Keras fast path (sm_100a, bf16 activations, NHWC).
+//
+// The stock-PyTorch rendition of the MNIST-CNN step launches 53 kernels, most of
+// them tiny elementwise / reduction kernels around the cuDNN/cuBLAS calls (bias
+// add, clamp, max-pool fwd/bwd, dropout, bias-gradient reductions, the softmax /
+// NLL chain, gradient accumulation adds) -- see profiles/launches_r1a_*.csv.
+// These kernels fuse each such chain into ONE launch and write parameter
+// gradients straight into the flat symmetric gradient buffer that the K4
+// reduce-scatter/optimizer/all-gather kernel consumes:
+//
+//   tfy_conv3x3_c1_fwd        direct 3x3 conv for C_in = 1 + bias + ReLU
+//   tfy_conv3x3_c1_wgrad      its weight gradient (reduction over all output pixels)
+//   tfy_bias_act_drop_fwd     y = dropout(act(z + bias)) over [rows, C], keep-mask byte
+//   tfy_act_drop_bwd_bias     dz = dy * mask (+ dbias[C] reduced and stored as bf16)
+//   tfy_bias_relu_pool_drop_fwd   z -> bias + ReLU + 2x2 max-pool + dropout (+1 code byte)
+//   tfy_pool_drop_relu_bwd        its backward (+ dbias[C])
+//   tfy_softmax_xent          logits(+bias) -> mean loss, dlogits = (softmax - onehot)/B, dbias, #correct
+//
+// Dropout randomness is counter based: hash(seed, layer salt, optimizer step, element) with the
+// step read from the device-resident TfyOptHyper, so a replayed CUDA graph draws fresh masks.
+#include "tfy_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t tfy_hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// uniform in [0,1) for (seed, step, index)
+__device__ __forceinline__ float tfy_uniform(uint32_t seed, uint32_t step, uint64_t idx) {
+    uint32_t h = tfy_hash32(seed ^ tfy_hash32(step * 0x9E3779B9U + 0x85ebca6bU) ^
+                            tfy_hash32((uint32_t)idx * 0xC2B2AE35U + (uint32_t)(idx >> 32) + 0x27d4eb2fU));
+    return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float bf16_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// Last-CTA finalisation of per-CTA partial column sums: partial[gridDim.x][C] fp32 -> out[C] bf16.
+// `counter` must be zero on entry and is reset to zero by the finishing CTA (replay safe).
+__device__ void tfy_finalize_colsum(const float* partial, int C, __nv_bfloat16* out, uint32_t* counter) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(counter, 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * C + c);
+        out[c] = __float2bfloat16(s);
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// conv 3x3, C_in = 1, stride 1, VALID, + bias + ReLU.   x: [B,H,W] (fp32 or bf16), w: [O][9] bf16,
+// y: [B,H-2,W-2,O] bf16.  One thread = one output pixel x 8 output channels (a 16-byte store).
+// ---------------------------------------------------------------------------------------------
+template <typename XT>
+__global__ void __launch_bounds__(256)
+tfy_conv3x3_c1_fwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                          const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                          int O) {
+    extern __shared__ float s_w[];  // [9][O] + [O] bias
+    for (int i = threadIdx.x; i < 9 * O; i += blockDim.x) {
+        const int o = i % O, t = i / O;
+        s_w[i] = bf16_to_f(w[o * 9 + t]);
+    }
+    for (int i = threadIdx.x; i < O; i += blockDim.x) s_w[9 * O + i] = bf16_to_f(bias[i]);
+    __syncthreads();
+    const int OH = H - 2, OW = W - 2, G = O / 8;
+    const size_t total = (size_t)B * OH * OW * G;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % G;
+        size_t pix = idx / G;
+        const int ow = pix % OW;
+        pix /= OW;
+        const int oh = pix % OH;
+        const int b = pix / OH;
+        const XT* xp = x + ((size_t)b * H + oh) * W + ow;
+        float xin[9];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) xin[kh * 3 + kw] = (float)xp[kh * W + kw];
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = s_w[9 * O + g * 8 + k];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(xin[t], s_w[t * O + g * 8 + k], acc[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaxf(acc[k], 0.f);
+        tfy_st16(y + (idx * 8), TfyPack<__nv_bfloat16>::pack(acc));
+    }
+}
+
+// dW[o][t] = sum over (b,oh,ow) x[b,oh+kh,ow+kw] * dz[b,oh,ow,o].  blockDim = 9*O threads
+// (thread -> (tap, o)); each CTA reduces a contiguous chunk of output pixels, partials are merged
+// by the last CTA and stored as bf16 [O][9].
+template <typename XT>
+__global__ void tfy_conv3x3_c1_wgrad_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                                            float* __restrict__ partial, __nv_bfloat16* __restrict__ dw,
+                                            uint32_t* counter, int B, int H, int W, int O) {
+    const int OH = H - 2, OW = W - 2;
+    const int t = threadIdx.x / O, o = threadIdx.x % O;
+    const int kh = t / 3, kw = t % 3;
+    const size_t npix = (size_t)B * OH * OW;
+    const size_t per = (npix + gridDim.x - 1) / gridDim.x;
+    const size_t p0 = per * blockIdx.x, p1 = min(npix, p0 + per);
+    float acc = 0.f;
+    for (size_t p = p0; p < p1; ++p) {
+        const int ow = p % OW;
+        const size_t r = p / OW;
+        const int oh = r % OH;
+        const int b = r / OH;
+        const float xv = (float)x[((size_t)b * H + oh + kh) * W + ow + kw];
+        acc = fmaf(xv, bf16_to_f(dz[p * O + o]), acc);
+    }
+    // partial layout [grid][O*9] in (o, tap) order == the [O][9] weight layout
+    partial[(size_t)blockIdx.x * (9 * O) + o * 9 + t] = acc;
+    tfy_finalize_colsum(partial, 9 * O, dw, counter);
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = dropout(act(z + bias[c])) over a [rows, C] bf16 matrix (C % 8 == 0); y may alias z.
+// mask (optional, 1 byte per element): 1 = gradient flows (act'(.) != 0 and kept).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tfy_bias_act_drop_fwd_kernel(const __nv_bfloat16* z, const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* y,
+                             uint8_t* __restrict__ mask, size_t rows, int C, int relu, float drop_rate, uint32_t seed,
+                             const TfyOptHyper* __restrict__ hp) {
+    const int G = C / 8;
+    const size_t total = rows * G;
+    const uint32_t step = hp ? (uint32_t)hp->step : 0u;
+    const float keep_scale = drop_rate > 0.f ? 1.f / (1.f - drop_rate) : 1.f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % G;
+        float v[8], bv[8];
+        TfyPack<__nv_bfloat16>::unpack(tfy_ld16(z + idx * 8), v);
+        if (bias) {
+            TfyPack<__nv_bfloat16>::unpack(tfy_ld16(bias + g * 8), bv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += bv[k];
+        }
+        uint32_t m_lo = 0, m_hi = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            bool on = true;
+            if (relu) { on = v[k] > 0.f; v[k] = on ? v[k] : 0.f; }
+            if (drop_rate > 0.f) {
+                const bool keep = tfy_uniform(seed, step, idx * 8 + k) >= drop_rate;
+                v[k] = keep ? v[k] * keep_scale : 0.f;
+                on = on && keep;
+            }
+            if (k < 4) m_lo |= (on ? 1u : 0u) << (8 * k);
+            else m_hi |= (on ? 1u : 0u) << (8 * (k - 4));
+        }
+        tfy_st16(y + idx * 8, TfyPack<__nv_bfloat16>::pack(v));
+        if (mask) *reinterpret_cast<uint2*>(mask + idx * 8) = make_uint2(m_lo, m_hi);
+    }
+}
+
+// dz = dy * gate * scale, where gate comes from `mask` bytes (if given) or from y > 0; dbias[c] = sum_rows dz.
+__global__ void __launch_bounds__(256)
+tfy_act_drop_bwd_bias_kernel(const __nv_bfloat16* dy, const uint8_t* __restrict__ mask,
+                             const __nv_bfloat16* __restrict__ y, __nv_bfloat16* dz, float scale, size_t rows, int C,
+                             float* __restrict__ partial, __nv_bfloat16* __restrict__ dbias, uint32_t* counter) {
+    extern __shared__ float s_sum[];  // [C]
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
+    __syncthreads();
+    const int G = C / 8;
+    const size_t total = rows * G;
+    // each thread keeps a fixed column group: stride must be a multiple of G
+    const size_t stride = ((size_t)gridDim.x * blockDim.x / G) * G;
+    float colacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = start < stride;
+    const int g = (int)(start % G);
+    if (active) {
+        for (size_t idx = start; idx < total; idx += stride) {
+            float v[8];
+            TfyPack<__nv_bfloat16>::unpack(tfy_ld16(dy + idx * 8), v);
+            if (mask) {
+                const uint2 m = *reinterpret_cast<const uint2*>(mask + idx * 8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t bit = (k < 4 ? (m.x >> (8 * k)) : (m.y >> (8 * (k - 4)))) & 1u;
+                    v[k] = bit ? v[k] * scale : 0.f;
+                }
+            } else if (y) {
+                float yv[8];
+                TfyPack<__nv_bfloat16>::unpack(tfy_ld16(y + idx * 8), yv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = yv[k] > 0.f ? v[k] * scale : 0.f;
+            }
+            if (dz) tfy_st16(dz + idx * 8, TfyPack<__nv_bfloat16>::pack(v));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) colacc[k] += v[k];
+        }
+    }
+    if (dbias) {
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[g * 8 + k], colacc[k]);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) partial[(size_t)blockIdx.x * C + c] = s_sum[c];
+        tfy_finalize_colsum(partial, C, dbias, counter);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// z [B,H,W,C] (conv output, pre-bias) -> p [B,H/2,W/2,C] = dropout(maxpool2x2(relu(z + bias)))
+// code byte per pooled element: bits 0-1 = argmax position (dy*2+dx), bit 2 = gradient flows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tfy_bias_relu_pool_drop_fwd_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ bias,
+                                   __nv_bfloat16* __restrict__ p, uint8_t* __restrict__ code, int B, int H, int W,
+                                   int C, float drop_rate, uint32_t seed, const TfyOptHyper* __restrict__ hp) {
+    const int PH = H / 2, PW = W / 2, G = C / 8;
+    const size_t total = (size_t)B * PH * PW * G;
+    const uint32_t step = hp ? (uint32_t)hp->step : 0u;
+    const float keep_scale = drop_rate > 0.f ? 1.f / (1.f - drop_rate) : 1.f;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int g = idx % G;
+        size_t r = idx / G;
+        const int pw = r % PW;
+        r /= PW;
+        const int ph = r % PH;
+        const int b = r / PH;
+        float bv[8], best[8];
+        int arg[8];
+        TfyPack<__nv_bfloat16>::unpack(tfy_ld16(bias + g * 8), bv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { best[k] = -3.0e38f; arg[k] = 0; }
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float v[8];
+                const size_t off = (((size_t)b * H + ph * 2 + dy) * W + pw * 2 + dx) * C + g * 8;
+                TfyPack<__nv_bfloat16>::unpack(tfy_ld16(z + off), v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (v[k] > best[k]) { best[k] = v[k]; arg[k] = dy * 2 + dx; }
+            }
+        uint32_t c_lo = 0, c_hi = 0;
+        float out[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = best[k] + bv[k];
+            bool on = v > 0.f;
+            v = on ? v : 0.f;
+            if (drop_rate > 0.f) {
+                const bool keep = tfy_uniform(seed, step, idx * 8 + k) >= drop_rate;
+                v = keep ? v * keep_scale : 0.f;
+                on = on && keep;
+            }
+            out[k] = v;
+            const uint32_t cb = (uint32_t)arg[k] | (on ? 4u : 0u);
+            if (k < 4) c_lo |= cb << (8 * k);
+            else c_hi |= cb << (8 * (k - 4));
+        }
+        tfy_st16(p + idx * 8, TfyPack<__nv_bfloat16>::pack(out));
+        *reinterpret_cast<uint2*>(code + idx * 8) = make_uint2(c_lo, c_hi);
+    }
+}
+
+// dp [B,PH,PW,C] + code -> dz [B,H,W,C] (gradient wrt the conv output), dbias[C] = sum dz.
+__global__ void __launch_bounds__(256)
+tfy_pool_drop_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dp, const uint8_t* __restrict__ code,
+                              __nv_bfloat16* __restrict__ dz, float scale, int B, int H, int W, int C,
+                              float* __restrict__ partial, __nv_bfloat16* __restrict__ dbias, uint32_t* counter) {
+    extern __shared__ float s_sum[];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
+    __syncthreads();
+    const int PH = H / 2, PW = W / 2, G = C / 8;
+    const size_t total = (size_t)B * PH * PW * G;
+    const size_t stride = ((size_t)gridDim.x * blockDim.x / G) * G;
+    const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = start < stride;
+    const int g = (int)(start % G);
+    float colacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+        for (size_t idx = start; idx < total; idx += stride) {
+            size_t r = idx / G;
+            const int pw = r % PW;
+            r /= PW;
+            const int ph = r % PH;
+            const int b = r / PH;
+            float d[8];
+            TfyPack<__nv_bfloat16>::unpack(tfy_ld16(dp + idx * 8), d);
+            const uint2 cd = *reinterpret_cast<const uint2*>(code + idx * 8);
+            int arg[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t cb = (k < 4 ? (cd.x >> (8 * k)) : (cd.y >> (8 * (k - 4)))) & 0xffu;
+                d[k] = (cb & 4u) ? d[k] * scale : 0.f;
+                arg[k] = cb & 3u;
+                colacc[k] += d[k];
+            }
+#pragma unroll
+            for (int pos = 0; pos < 4; ++pos) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = arg[k] == pos ? d[k] : 0.f;
+                const size_t off = (((size_t)b * H + ph * 2 + (pos >> 1)) * W + pw * 2 + (pos & 1)) * C + g * 8;
+                tfy_st16(dz + off, TfyPack<__nv_bfloat16>::pack(o));
+            }
+        }
+    }
+    if (dbias) {
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[g * 8 + k], colacc[k]);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) partial[(size_t)blockIdx.x * C + c] = s_sum[c];
+        tfy_finalize_colsum(partial, C, dbias, counter);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// softmax cross-entropy head.  logits [B,C] bf16 (+ optional bias[C]), labels int64.
+// Single CTA (B rows strided over the threads): loss = mean CE (fp32), dlogits = (softmax-onehot)/B
+// (bf16), dbias[C] = column sums of dlogits (bf16), stats[0] += #correct, stats[1] += B.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+tfy_softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16* __restrict__ bias,
+                        const long long* __restrict__ labels, float* __restrict__ loss,
+                        __nv_bfloat16* __restrict__ dlogits, __nv_bfloat16* __restrict__ dbias,
+                        float* __restrict__ stats, int B, int C) {
+    extern __shared__ float sm[];  // [C] dbias accumulators + [2] loss, correct
+    float* s_db = sm;
+    float* s_red = sm + C;
+    for (int c = threadIdx.x; c < C + 2; c += blockDim.x) sm[c] = 0.f;
+    __syncthreads();
+    const float invB = 1.f / (float)B;
+    float my_loss = 0.f, my_correct = 0.f;
+    for (int r = threadIdx.x; r < B; r += blockDim.x) {
+        const __nv_bfloat16* row = logits + (size_t)r * C;
+        float mx = -3.0e38f;
+        int amax = 0;
+        for (int c = 0; c < C; ++c) {
+            const float v = bf16_to_f(row[c]) + (bias ? bf16_to_f(bias[c]) : 0.f);
+            if (v > mx) { mx = v; amax = c; }
+        }
+        float se = 0.f;
+        for (int c = 0; c < C; ++c) se += __expf(bf16_to_f(row[c]) + (bias ? bf16_to_f(bias[c]) : 0.f) - mx);
+        const float lse = mx + __logf(se);
+        const int lab = (int)labels[r];
+        const float inv_se = 1.f / se;
+        for (int c = 0; c < C; ++c) {
+            const float v = bf16_to_f(row[c]) + (bias ? bf16_to_f(bias[c]) : 0.f);
+            const float prob = __expf(v - mx) * inv_se;
+            const float d = (prob - (c == lab ? 1.f : 0.f)) * invB;
+            if (c == lab) my_loss += lse - v;
+            dlogits[(size_t)r * C + c] = __float2bfloat16(d);
+            if (dbias) atomicAdd(&s_db[c], d);
+        }
+        my_correct += (amax == lab) ? 1.f : 0.f;
+    }
+    atomicAdd(&s_red[0], my_loss);
+    atomicAdd(&s_red[1], my_correct);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *loss = s_red[0] * invB;
+        if (stats) { stats[0] += s_red[1]; stats[1] += (float)B; }
+    }
+    if (dbias)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) dbias[c] = __float2bfloat16(s_db[c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static inline int tfy_grid_for(size_t items, int block, int cap) {
+    size_t g = (items + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > (size_t)cap) g = cap;
+    return (int)g;
+}
+
+extern "C" {
+
+// scratch: fp32 workspace of at least tfy_nn_scratch_floats(...) floats; counter: zero-initialised u32
+size_t tfy_nn_max_partial_blocks() { return 592; }
+
+int tfy_conv3x3_c1_fwd(const void* x, int x_is_f32, const void* w, const void* bias, void* y, int B, int H, int W,
+                       int O, cudaStream_t s) {
+    if (O % 8) return -2;
+    const size_t total = (size_t)B * (H - 2) * (W - 2) * (O / 8);
+    const int grid = tfy_grid_for(total, 256, 148 * 8);
+    const size_t smem = (size_t)(10 * O) * sizeof(float);
+    if (x_is_f32)
+        tfy_conv3x3_c1_fwd_kernel<float><<<grid, 256, smem, s>>>((const float*)x, (const __nv_bfloat16*)w,
+                                                                  (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, B, H,
+                                                                  W, O);
+    else
+        tfy_conv3x3_c1_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, B, H, W, O);
+    return (int)cudaGetLastError();
+}
+
+int tfy_conv3x3_c1_wgrad(const void* x, int x_is_f32, const void* dz, float* partial, void* dw, uint32_t* counter,
+                         int B, int H, int W, int O, cudaStream_t s) {
+    if (9 * O > 1024) return -2;
+    const int grid = 592;
+    if (x_is_f32)
+        tfy_conv3x3_c1_wgrad_kernel<float><<<grid, 9 * O, 0, s>>>((const float*)x, (const __nv_bfloat16*)dz, partial,
+                                                                   (__nv_bfloat16*)dw, counter, B, H, W, O);
+    else
+        tfy_conv3x3_c1_wgrad_kernel<__nv_bfloat16><<<grid, 9 * O, 0, s>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, partial, (__nv_bfloat16*)dw, counter, B, H, W, O);
+    return (int)cudaGetLastError();
+}
+
+int tfy_bias_act_drop_fwd(const void* z, const void* bias, void* y, void* mask, size_t rows, int C, int relu,
+                          float drop_rate, uint32_t seed, const TfyOptHyper* hp, cudaStream_t s) {
+    if (C % 8) return -2;
+    const int grid = tfy_grid_for(rows * (C / 8), 256, 148 * 8);
+    tfy_bias_act_drop_fwd_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)bias,
+                                                      (__nv_bfloat16*)y, (uint8_t*)mask, rows, C, relu, drop_rate,
+                                                      seed, hp);
+    return (int)cudaGetLastError();
+}
+
+int tfy_act_drop_bwd_bias(const void* dy, const void* mask, const void* y, void* dz, float scale, size_t rows, int C,
+                          float* partial, void* dbias, uint32_t* counter, cudaStream_t s) {
+    if (C % 8) return -2;
+    int grid = tfy_grid_for(rows * (C / 8), 256, 592);
+    // the kernel needs gridDim*blockDim >= C/8 so that every column group has a thread
+    if ((size_t)grid * 256 < (size_t)(C / 8)) grid = (C / 8 + 255) / 256;
+    tfy_act_drop_bwd_bias_kernel<<<grid, 256, C * sizeof(float), s>>>(
+        (const __nv_bfloat16*)dy, (const uint8_t*)mask, (const __nv_bfloat16*)y, (__nv_bfloat16*)dz, scale, rows, C,
+        partial, (__nv_bfloat16*)dbias, counter);
+    return (int)cudaGetLastError();
+}
+
+int tfy_bias_relu_pool_drop_fwd(const void* z, const void* bias, void* p, void* code, int B, int H, int W, int C,
+                                float drop_rate, uint32_t seed, const TfyOptHyper* hp, cudaStream_t s) {
+    if (C % 8 || H % 2 || W % 2) return -2;
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+    const int grid = tfy_grid_for(total, 256, 148 * 8);
+    tfy_bias_relu_pool_drop_fwd_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)bias,
+                                                            (__nv_bfloat16*)p, (uint8_t*)code, B, H, W, C, drop_rate,
+                                                            seed, hp);
+    return (int)cudaGetLastError();
+}
+
+int tfy_pool_drop_relu_bwd(const void* dp, const void* code, void* dz, float scale, int B, int H, int W, int C,
+                           float* partial, void* dbias, uint32_t* counter, cudaStream_t s) {
+    if (C % 8 || H % 2 || W % 2) return -2;
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+    int grid = tfy_grid_for(total, 256, 592);
+    tfy_pool_drop_relu_bwd_kernel<<<grid, 256, C * sizeof(float), s>>>(
+        (const __nv_bfloat16*)dp, (const uint8_t*)code, (__nv_bfloat16*)dz, scale, B, H, W, C, partial,
+        (__nv_bfloat16*)dbias, counter);
+    return (int)cudaGetLastError();
+}
+
+int tfy_softmax_xent(const void* logits, const void* bias, const void* labels, float* loss, void* dlogits,
+                     void* dbias, float* stats, int B, int C, cudaStream_t s) {
+    int block = B < 1024 ? ((B + 31) / 32) * 32 : 1024;
+    if (block < 32) block = 32;
+    tfy_softmax_xent_kernel<<<1, block, (C + 2) * sizeof(float), s>>>(
+        (const __nv_bfloat16*)logits, (const __nv_bfloat16*)bias, (const long long*)labels, loss,
+        (__nv_bfloat16*)dlogits, (__nv_bfloat16*)dbias, stats, B, C);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
