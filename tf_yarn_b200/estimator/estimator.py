@@ -214,7 +214,13 @@ class Estimator:
         use_ps = cluster.has_ps and cluster.task_type in ("chief", "worker")
         self._restore()
         if use_ps and self._ps is None and self._network is not None:
-            self._ps = ps_mod.connect_worker(self._network, self._opt_desc, cluster, is_chief, self._global_step)
+            if self._device.type == "cuda":
+                from tf_yarn_b200.estimator import ps_hbm
+                self._ps = ps_hbm.connect_worker(self._network, self._opt_desc, cluster, is_chief,
+                                                 self._global_step)
+            else:
+                self._ps = ps_mod.connect_worker(self._network, self._opt_desc, cluster, is_chief,
+                                                 self._global_step)
             if not is_chief:
                 self._global_step = self._ps.global_step()
         if self._pending_broadcast is not None:
@@ -236,7 +242,7 @@ class Estimator:
 
         ctx = SessionRunContext(self, self._global_step)
         start_step = self._global_step
-        last_save_time = time.time()
+        last_save_time, last_save_step = time.time(), self._global_step
         last_log_time, last_log_step = time.time(), self._global_step
         item = first
         if self._network is not None:
@@ -248,6 +254,7 @@ class Estimator:
                 break
             features, labels = _split(item)
             wants_step = [h for h in hooks if _wants_global_step(h.before_run(ctx))]
+            prev_gs = self._global_step
             loss = self._train_step(features, labels, distributed)
             if self._ps is not None:
                 self._global_step = self._ps.increment_global_step()
@@ -257,7 +264,8 @@ class Estimator:
             for h in hooks:
                 h.after_run(ctx, SessionRunValues(results=self._global_step if h in wants_step else None))
             gs = self._global_step
-            if writer is not None and cfg.save_summary_steps and gs % cfg.save_summary_steps == 0:
+            if writer is not None and cfg.save_summary_steps and \
+                    gs // cfg.save_summary_steps > (gs - 1 if self._ps is None else prev_gs) // cfg.save_summary_steps:
                 self.last_loss = float(loss)
                 writer.add_scalar("loss", self.last_loss, gs)
             if cfg.log_step_count_steps and gs - last_log_step >= cfg.log_step_count_steps:
@@ -269,11 +277,14 @@ class Estimator:
                     writer.add_scalar("global_step/sec", sps, gs)
                 last_log_time, last_log_step = now, gs
             if writes_files:
-                due = (cfg.save_checkpoints_steps and gs % cfg.save_checkpoints_steps == 0) or \
+                # with asynchronous workers the chief sees the global step advance by several units
+                # per local step: trigger on crossing a multiple, not on hitting it exactly
+                due = (cfg.save_checkpoints_steps and
+                       gs // cfg.save_checkpoints_steps > last_save_step // cfg.save_checkpoints_steps) or \
                       (cfg.save_checkpoints_secs and time.time() - last_save_time >= cfg.save_checkpoints_secs)
                 if due:
                     self._save()
-                    last_save_time = time.time()
+                    last_save_time, last_save_step = time.time(), gs
             if ctx.stop_requested:
                 break
             item = next(it, None)

@@ -1,0 +1,341 @@
+"""B200 data plane of the asynchronous parameter server: shards in the ps ranks' HBM.
+
+Every task of the training cluster (chief, workers AND ps) joins one symmetric arena
+(:mod:`tf_yarn_b200.parallel.symm`, rendezvous through the launcher's KV store).  A ps rank's
+shard is a region of ITS arena; chief/workers reach it through the peer mapping over NVLink:
+
+* dense pull   : ``tfy_ps_pull``   -- peer fp32 master -> local replica, one launch for all variables;
+* GEMM pull    : ``tfy_gemm_bf16`` -- the weight matrix of a Dense layer is never copied: its bf16
+  shadow on the ps rank is streamed by TMA into the tcgen05 GEMM that consumes it (K5);
+* sparse pull  : ``tfy_ps_embedding_bag`` -- rows of the batch gathered from the peer table and
+  bag-reduced in the same kernel;
+* push         : ``tfy_ps_push`` / ``tfy_ps_push_rows`` -- gradients applied to the peer master with
+  vector red/atom (SGD, Adagrad), asynchronously and without locks (K6).
+
+The ps process only owns memory and waits for the stop barrier: no server thread is on the data path.
+Control state (layout, readiness, global step) stays on the KV store / a shared-memory header, as in
+the CPU data plane (:mod:`tf_yarn_b200.estimator.ps`).
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import os
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from tf_yarn_b200 import _task_commons
+from tf_yarn_b200.estimator import ps as ps_cpu
+from tf_yarn_b200.ops import native
+from tf_yarn_b200.parallel.symm import _RawCudaMemory
+
+logger = logging.getLogger(__name__)
+
+_vp, _i, _sz, _f, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_longlong
+native.declare("tfy_ps_pull", [_vp, _i, _sz, _i, _vp])
+native.declare("tfy_ps_push", [_vp, _i, _sz, _i, _i, _f, _f, _f, _f, _vp])
+native.declare("tfy_ps_refresh_shadow", [_vp, _i, _sz, _vp])
+native.declare("tfy_ps_embedding_bag", [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp])
+native.declare("tfy_ps_push_rows", [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _i, _f, _f, _f, _vp])
+
+OPT_CODES = {"sgd": native.OPT_SGD, "adagrad": native.OPT_ADAGRAD}
+
+
+class PsSeg(ctypes.Structure):
+    _fields_ = [("remote_w", ctypes.c_uint64), ("remote_s1", ctypes.c_uint64), ("remote_shadow", ctypes.c_uint64),
+                ("local", ctypes.c_uint64), ("n", ctypes.c_uint64)]
+
+
+def cluster_ranks(cluster) -> Dict[str, int]:
+    """Global rank of every cluster task in the symmetric arena: chief, workers, then ps."""
+    keys = cluster.trainers() + [f"ps:{i}" for i in range(len(cluster.spec.get("ps", [])))]
+    return {k: r for r, k in enumerate(keys)}
+
+
+def join_arena(cluster):
+    """Create this process's Communicator over ALL cluster tasks (collective: every task calls it)."""
+    from tf_yarn_b200.parallel import runtime
+    ranks = cluster_ranks(cluster)
+    me = f"{cluster.task_type}:{cluster.task_id}"
+    os.environ["TFY_RANK"] = str(ranks[me])
+    os.environ["TFY_WORLD_SIZE"] = str(len(ranks))
+    ids = [int(v) for v in os.environ.get("TFY_GPU_IDS", "").split(",") if v.strip() != ""]
+    dev = ids[0] if ids else ranks[me] % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    return runtime.get_communicator(device=dev), ranks
+
+
+def shard_bytes(layout: ps_cpu.Layout) -> int:
+    """Bytes every rank reserves in its arena (the largest shard; fp32 master+slots, then bf16 shadows)."""
+    worst = 0
+    for ps in range(layout.n_ps):
+        elems = layout.shard_elems[ps]
+        worst = max(worst, elems * 4 + elems * 2 + 4096)
+    return (worst + 4095) // 4096 * 4096
+
+
+class HbmConnection:
+    """Chief / worker view of the HBM shards."""
+
+    def __init__(self, layout: ps_cpu.Layout, comm, ranks: Dict[str, int], region_off: int, names: List[str],
+                 header: ps_cpu.ShmShard, network: nn.Module):
+        self.layout, self.comm, self.names, self.header = layout, comm, names, header
+        self.lib = native.load()
+        self.opt = OPT_CODES.get(layout.opt_kind)
+        if self.opt is None:
+            raise ValueError(f"the HBM parameter server fuses SGD and Adagrad; got {layout.opt_kind!r}")
+        arena = comm.arena
+        self.ps_base = [arena.peer_base[ranks[f"ps:{i}"]] + region_off for i in range(layout.n_ps)]
+        self.region_bytes = shard_bytes(layout)
+        dev = torch.device(f"cuda:{comm.device}")
+        self.device = dev
+        params = dict(network.named_parameters())
+        self.params = [params[n] for n in names]
+        self.sparse: Dict[int, nn.Module] = {}      # variable index -> EmbeddingBag served sparsely
+        self.gemm: Dict[int, nn.Module] = {}        # variable index -> Linear whose weight stays remote
+        self._classify(network)
+        self.dense_idx = [i for i in range(len(names)) if i not in self.sparse]
+        self._pull_segs = self._make_segs(for_push=False)
+        self._push_segs = None
+        self._push_ptrs = None
+        self._max_n = max([self._n4(i) for i in self.dense_idx] + [4])
+        self.pull_stream = torch.cuda.Stream(device=dev)
+        self._pull_done: Optional[torch.cuda.Event] = None
+        h = layout.hyper
+        self.lr, self.eps, self.wd = float(h["lr"]), float(h["eps"]), float(h["wd"])
+
+    # ------------------------------------------------------------------ addressing
+    def _n4(self, i: int) -> int:
+        return (self.layout.numel[i] + 3) // 4 * 4
+
+    def master_ptr(self, i: int, slot: int = 0) -> int:
+        lay = self.layout
+        return self.ps_base[lay.owner[i]] + 4 * (lay.offset[i] + slot * lay.padded(i))
+
+    def shadow_ptr(self, i: int) -> int:
+        """bf16 shadow of variable i: the shadows of a ps follow its fp32 area (master + slots)."""
+        lay = self.layout
+        ps = lay.owner[i]
+        return self.ps_base[ps] + 4 * lay.shard_elems[ps] + 2 * self._shadow_off(i)
+
+    def _shadow_off(self, i: int) -> int:
+        """Element offset of variable i inside its ps's bf16 shadow area (padded sizes, layout order)."""
+        lay = self.layout
+        off = 0
+        for j in range(i):
+            if lay.owner[j] == lay.owner[i]:
+                off += lay.padded(j)
+        return off
+
+    def remote_tensor(self, i: int, slot: int = 0) -> torch.Tensor:
+        """Zero-copy torch view of a peer region (used for initialisation and checkpoints)."""
+        n = self.layout.numel[i]
+        mem = _RawCudaMemory(self.master_ptr(i, slot), n * 4, self)
+        return torch.as_tensor(mem, device=self.device).view(torch.float32)
+
+    def _classify(self, network: nn.Module) -> None:
+        by_param = {id(p): i for i, p in enumerate(self.params)}
+        for mod in network.modules():
+            if isinstance(mod, nn.EmbeddingBag) and id(mod.weight) in by_param and mod.embedding_dim % 4 == 0 \
+                    and mod.mode in ("sum", "mean"):
+                self.sparse[by_param[id(mod.weight)]] = mod
+            elif isinstance(mod, nn.Linear) and id(mod.weight) in by_param and mod.in_features % 8 == 0:
+                self.gemm[by_param[id(mod.weight)]] = mod
+
+    def _make_segs(self, for_push: bool):
+        segs = (PsSeg * max(1, len(self.dense_idx)))()
+        for k, i in enumerate(self.dense_idx):
+            p = self.params[i]
+            segs[k].remote_w = self.master_ptr(i)
+            segs[k].remote_s1 = self.master_ptr(i, 1) if self.layout.slots >= 1 else 0
+            segs[k].remote_shadow = self.shadow_ptr(i) if i in self.gemm else 0
+            segs[k].local = (p.grad.data_ptr() if for_push else p.data_ptr())
+            segs[k].n = self.layout.numel[i]
+        dev_segs = torch.frombuffer(bytearray(bytes(segs)), dtype=torch.uint8).to(self.device)
+        return dev_segs
+
+    # ------------------------------------------------------------------ install the fused ops
+    def install(self, network: nn.Module) -> None:
+        """Route EmbeddingBag / Linear modules through the peer-memory kernels."""
+        conn = self
+        for idx, mod in self.sparse.items():
+            mod.forward = _make_bag_forward(conn, idx, mod)
+        for idx, mod in self.gemm.items():
+            mod.forward = _make_linear_forward(conn, idx, mod)
+
+    # ------------------------------------------------------------------ pull / push
+    def pull(self, network: nn.Module) -> None:
+        """Start the dense pull on the side stream; forward GEMMs read their weights remotely meanwhile."""
+        if not self.dense_idx:
+            return
+        for i in self.dense_idx:           # local replicas must be 16-byte aligned, contiguous fp32
+            assert self.params[i].dtype == torch.float32
+        self.pull_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.pull_stream):
+            native.check(self.lib.tfy_ps_pull(self._pull_segs.data_ptr(), len(self.dense_idx), self._max_n, 0,
+                                              self.pull_stream.cuda_stream), "tfy_ps_pull")
+            self._pull_done = torch.cuda.Event()
+            self._pull_done.record(self.pull_stream)
+        # everything except the remote-GEMM layers needs the replica right away
+        torch.cuda.current_stream().wait_event(self._pull_done)
+
+    def push(self, network: nn.Module) -> None:
+        if not self.dense_idx:
+            return
+        for i in self.dense_idx:
+            p = self.params[i]
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        ptrs = tuple(self.params[i].grad.data_ptr() for i in self.dense_idx)
+        if self._push_segs is None or self._push_ptrs != ptrs:     # gradients normally keep their address
+            self._push_segs, self._push_ptrs = self._make_segs(for_push=True), ptrs
+        segs = self._push_segs
+        native.check(self.lib.tfy_ps_push(segs.data_ptr(), len(self.dense_idx), self._max_n, 0, self.opt, self.lr,
+                                          self.eps, self.wd, 1.0, torch.cuda.current_stream().cuda_stream),
+                     "tfy_ps_push")
+
+    def refresh_shadows(self) -> None:
+        segs = self._make_segs(for_push=False)
+        native.check(self.lib.tfy_ps_refresh_shadow(segs.data_ptr(), len(self.dense_idx), self._max_n,
+                                                    torch.cuda.current_stream().cuda_stream), "tfy_ps_refresh_shadow")
+        torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------ global step / checkpoints
+    def increment_global_step(self) -> int:
+        return self.header.add_global_step(1)
+
+    def global_step(self) -> int:
+        return self.header.global_step()
+
+    def state_dict_from_ps(self, network: nn.Module) -> Dict[str, torch.Tensor]:
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for i, p in enumerate(self.params):
+                p.copy_(self.remote_tensor(i).view(p.shape))
+        return network.state_dict()
+
+
+def _make_bag_forward(conn: HbmConnection, idx: int, mod: nn.EmbeddingBag):
+    lib = conn.lib
+    V, D = mod.num_embeddings, mod.embedding_dim
+    mean = 1 if mod.mode == "mean" else 0
+
+    class _Bag(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, ids, anchor):
+            ids = ids.contiguous().long()
+            B, L = ids.shape
+            out = torch.empty((B, D), dtype=torch.float32, device=ids.device)
+            native.check(lib.tfy_ps_embedding_bag(conn.master_ptr(idx), ids.data_ptr(), out.data_ptr(), 0, B, L, D, V,
+                                                  mean, torch.cuda.current_stream().cuda_stream),
+                         "tfy_ps_embedding_bag")
+            ctx.ids = ids
+            return out
+
+        @staticmethod
+        def backward(ctx, dout):
+            ids = ctx.ids
+            B, L = ids.shape
+            dout = dout.contiguous().float()
+            acc = conn.master_ptr(idx, 1) if conn.layout.slots >= 1 else None
+            native.check(lib.tfy_ps_push_rows(conn.master_ptr(idx), acc, ids.data_ptr(), dout.data_ptr(), 0, B, L, D,
+                                              V, mean, conn.opt, conn.lr, conn.eps, 1.0,
+                                              torch.cuda.current_stream().cuda_stream), "tfy_ps_push_rows")
+            return None, None
+
+    anchor = torch.zeros((), device=conn.device, requires_grad=True)
+
+    def forward(ids, offsets=None, per_sample_weights=None):
+        return _Bag.apply(ids, anchor)
+    return forward
+
+
+def _make_linear_forward(conn: HbmConnection, idx: int, mod: nn.Linear):
+    from tf_yarn_b200.ops.gemm import gemm_bf16
+    N, K = mod.out_features, mod.in_features
+    shadow = conn.shadow_ptr(idx)
+
+    class _PSLinear(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, weight, bias):
+            xb = x.to(torch.bfloat16).contiguous()
+            y = gemm_bf16(xb, None, bias=bias.to(torch.bfloat16) if bias is not None else None, b_ptr=shadow,
+                          b_rows=N, b_ld=K)                     # weights stream from the ps rank over NVLink
+            ctx.save_for_backward(xb, weight)
+            ctx.has_bias = bias is not None
+            return y.to(x.dtype)
+
+        @staticmethod
+        def backward(ctx, dy):
+            xb, weight = ctx.saved_tensors
+            dyf = dy.float()
+            dw = dyf.t() @ xb.float()
+            dx = dyf @ weight.float()                          # local replica, pulled on the side stream
+            db = dyf.sum(0) if ctx.has_bias else None
+            return dx.to(dy.dtype), dw.to(weight.dtype), db
+
+    def forward(x):
+        return _PSLinear.apply(x, mod.weight, mod.bias)
+    return forward
+
+
+# ---------------------------------------------------------------------------------------------
+# connection set-up (collective over the cluster)
+# ---------------------------------------------------------------------------------------------
+def connect_worker(network: nn.Module, opt_desc, cluster, is_chief: bool, global_step: int) -> HbmConnection:
+    client = _task_commons.TaskClient.from_current()
+    kv = client.kv
+    n_ps = len(cluster.spec["ps"])
+    named = ps_cpu._named_trainables(network)
+    names = [n for n, _ in named]
+    if is_chief:
+        layout = ps_cpu.Layout([(n, list(p.shape)) for n, p in named], n_ps, opt_desc.to_spec().kind,
+                               ps_cpu._hyper_of(opt_desc))
+        kv[ps_cpu.KV_LAYOUT] = layout.to_json().encode()
+    else:
+        layout = ps_cpu.Layout.from_json(kv.wait(ps_cpu.KV_LAYOUT))
+    comm, ranks = join_arena(cluster)
+    region_off = comm.arena.alloc(shard_bytes(layout), align=4096)
+    header_path = kv.wait("ps:0/shard").decode()
+    header = ps_cpu.ShmShard(header_path, 8, create=False)
+    conn = HbmConnection(layout, comm, ranks, region_off, names, header, network)
+    if is_chief:
+        with torch.no_grad():
+            for i, (_, p) in enumerate(named):
+                conn.remote_tensor(i).copy_(p.detach().reshape(-1).float())
+                if layout.opt_kind == "adagrad":
+                    conn.remote_tensor(i, 1).fill_(layout.hyper["init_s1"])
+        conn.refresh_shadows()
+        header.set_global_step(global_step)
+        torch.cuda.synchronize()
+        kv[ps_cpu.KV_READY] = b"1"
+        logger.info("HBM parameter servers initialised: %d variables on %d ps (%d sparse, %d remote-GEMM)",
+                    len(names), n_ps, len(conn.sparse), len(conn.gemm))
+    else:
+        kv.wait(ps_cpu.KV_READY)
+    conn.install(network)
+    return conn
+
+
+def serve(cluster, poll_secs: float = 0.2) -> None:
+    """``ps`` task on B200: join the arena, reserve the shard region, publish the header, idle."""
+    import time
+    client = _task_commons.TaskClient.from_current()
+    kv = client.kv
+    idx = cluster.task_id
+    layout = ps_cpu.Layout.from_json(kv.wait(ps_cpu.KV_LAYOUT))
+    comm, _ = join_arena(cluster)
+    off = comm.arena.alloc(shard_bytes(layout), align=4096)
+    region = comm.arena.tensor(off, (shard_bytes(layout),), torch.uint8)
+    region.zero_()
+    torch.cuda.synchronize()
+    path = os.path.join(ps_cpu._shm_dir(), f"tfy_ps_{ps_cpu._job_tag()}_{idx}")
+    header = ps_cpu.ShmShard(path, 8, create=True)
+    kv[f"ps:{idx}/shard"] = path.encode()
+    logger.info("ps %d: %d bytes of HBM shard at arena offset %d", idx, shard_bytes(layout), off)
+    import atexit
+    atexit.register(header.unlink)
+    while True:
+        time.sleep(poll_secs)

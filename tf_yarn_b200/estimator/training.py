@@ -69,6 +69,10 @@ def train_and_evaluate(estimator, train_spec: TrainSpec, eval_spec: EvalSpec):
     cluster = ClusterInfo.from_env()
     role = cluster.task_type
     if cluster.distributed and role == "ps":
+        import torch
+        if torch.cuda.is_available() and os.environ.get("TFY_GPU_IDS"):
+            from tf_yarn_b200.estimator import ps_hbm
+            ps_hbm.serve(cluster)  # never returns
         from tf_yarn_b200.estimator import ps
         ps.serve(cluster)          # never returns
         return None

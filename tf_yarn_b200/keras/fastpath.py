@@ -163,6 +163,7 @@ class FastSequentialEngine(GraphTrainEngine):
         self.stream.synchronize()
 
     # ------------------------------------------------------------------ the step
+    @torch.no_grad()
     def _forward_backward(self, x, y) -> None:
         lib, s = self.lib, self._s()
         self._k = 0

@@ -255,11 +255,21 @@ tfy_fused_step_kernel(TfyCommCtx c, uint64_t grad_off, uint64_t param_off, size_
     if (MODE != TFY_MODE_LOCAL) tfy_block_barrier(c);  // updated params visible on every rank
 
     if (zero_grads) {
-        // peers are done reading my gradient replica: clear it for the next accumulation
-        const size_t total_packs = shard_n * (size_t)(MODE == TFY_MODE_LOCAL ? 1 : c.world) * sizeof(GT) / 16;
-        uint4 z = make_uint4(0, 0, 0, 0);
+        // Clear the gradient replica for the next accumulation.  A CTA may only clear what is known
+        // to be consumed: after the exit barrier the same-index CTA of EVERY rank has finished, and
+        // those CTAs read (from all replicas, mine included) exactly the groups `tid + k*nthreads`
+        // of each rank's shard.  So this thread clears those groups of every shard in the LOCAL
+        // replica -- never data another local CTA's peers may still be reading.
+        const uint4 z = make_uint4(0, 0, 0, 0);
         char* gb = reinterpret_cast<char*>(c.peer_base[c.rank] + grad_off);
-        for (size_t i = tid; i < total_packs; i += nthreads) tfy_st16(gb + i * 16, z);
+        const int nshards = (MODE == TFY_MODE_LOCAL) ? 1 : c.world;
+        for (int r = 0; r < nshards; ++r) {
+            for (size_t g8 = tid; g8 < groups; g8 += nthreads) {
+                char* p = gb + ((size_t)r * shard_n + g8 * 8) * sizeof(GT);
+#pragma unroll
+                for (int k = 0; k < NG; ++k) tfy_st16(p + k * 16, z);
+            }
+        }
     }
 
     // advance the device-side step counter exactly once per launch

@@ -37,7 +37,10 @@ __device__ __forceinline__ float bf16_to_f(__nv_bfloat16 v) { return __bfloat162
 
 // Last-CTA finalisation of per-CTA partial column sums: partial[gridDim.x][C] fp32 -> out[C] bf16.
 // `counter` must be zero on entry and is reset to zero by the finishing CTA (replay safe).
-__device__ void tfy_finalize_colsum(const float* partial, int C, __nv_bfloat16* out, uint32_t* counter) {
+// The finishing CTA sums in parallel: thread (r, c) accumulates the CTAs b = r, r+R, ... of column c,
+// then the R partial results per column are combined through shared memory (`scratch`, >= blockDim floats).
+__device__ void tfy_finalize_colsum(const float* partial, int C, __nv_bfloat16* out, uint32_t* counter,
+                                    float* scratch) {
     __shared__ bool is_last;
     __threadfence();
     __syncthreads();
@@ -48,19 +51,58 @@ __device__ void tfy_finalize_colsum(const float* partial, int C, __nv_bfloat16* 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int nthr = blockDim.x;
+    for (int c0 = 0; c0 < C; c0 += nthr) {
+        const int cols = min(C - c0, nthr);
+        const int R = nthr / cols;                      // row-slices working on this column chunk
+        const int r = threadIdx.x / cols, c = threadIdx.x % cols;
         float s = 0.f;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(partial + (size_t)b * C + c);
-        out[c] = __float2bfloat16(s);
+        if (r < R)
+            for (unsigned b = r; b < gridDim.x; b += R) s += __ldcg(partial + (size_t)b * C + c0 + c);
+        __syncthreads();
+        scratch[threadIdx.x] = (r < R) ? s : 0.f;
+        __syncthreads();
+        if (threadIdx.x < cols) {
+            float t = 0.f;
+            for (int rr = 0; rr < R; ++rr) t += scratch[rr * cols + threadIdx.x];
+            out[c0 + threadIdx.x] = __float2bfloat16(t);
+        }
     }
     if (threadIdx.x == 0) *counter = 0;
+}
+
+// Per-CTA column sums of values held 8-per-thread (column group g of G = C/8): reduce the lanes of a
+// warp that share a group with shuffles, combine the warps through shared memory (s_sum: [C] floats,
+// zeroed by the caller before use), then publish this CTA's row of `partial`.
+__device__ __forceinline__ void tfy_block_colsum(float (&colacc)[8], int g, int G, bool active, float* s_sum, int C,
+                                                 float* partial_row) {
+    if (G < 32 && (32 % G) == 0 && (blockDim.x % 32) == 0) {
+        // lanes l and l + k*G of a warp hold the same column group (the grid stride keeps g = tid % G)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = active ? colacc[k] : 0.f;
+            for (int off = G; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            colacc[k] = v;
+        }
+        if ((threadIdx.x & 31) < G) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[g * 8 + k], colacc[k]);
+        }
+    } else if (active) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[g * 8 + k], colacc[k]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) partial_row[c] = s_sum[c];
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
 // conv 3x3, C_in = 1, stride 1, VALID, + bias + ReLU.   x: [B,H,W] (fp32 or bf16), w: [O][9] bf16,
-// y: [B,H-2,W-2,O] bf16.  One thread = one output pixel x 8 output channels (a 16-byte store).
+// y: [B,H-2,W-2,O] bf16.  One thread = one output pixel, all O channels: x loads are coalesced across
+// the warp, the weights are warp-broadcast reads from shared memory, each thread writes O*2 contiguous
+// bytes.
 // ---------------------------------------------------------------------------------------------
 template <typename XT>
 __global__ void __launch_bounds__(256)
@@ -74,60 +116,76 @@ tfy_conv3x3_c1_fwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restr
     }
     for (int i = threadIdx.x; i < O; i += blockDim.x) s_w[9 * O + i] = bf16_to_f(bias[i]);
     __syncthreads();
-    const int OH = H - 2, OW = W - 2, G = O / 8;
-    const size_t total = (size_t)B * OH * OW * G;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        const int g = idx % G;
-        size_t pix = idx / G;
+    const int OH = H - 2, OW = W - 2;
+    const size_t total = (size_t)B * OH * OW;
+    for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+         pix += (size_t)gridDim.x * blockDim.x) {
         const int ow = pix % OW;
-        pix /= OW;
-        const int oh = pix % OH;
-        const int b = pix / OH;
+        const size_t r = pix / OW;
+        const int oh = r % OH;
+        const int b = r / OH;
         const XT* xp = x + ((size_t)b * H + oh) * W + ow;
         float xin[9];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) xin[kh * 3 + kw] = (float)xp[kh * W + kw];
-        float acc[8];
+        __nv_bfloat16* yp = y + pix * O;
+        for (int g = 0; g < O; g += 8) {
+            float acc[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = s_w[9 * O + g * 8 + k];
+            for (int k = 0; k < 8; ++k) acc[k] = s_w[9 * O + g + k];
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
+            for (int t = 0; t < 9; ++t)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = fmaf(xin[t], s_w[t * O + g * 8 + k], acc[k]);
+                for (int k = 0; k < 8; ++k) acc[k] = fmaf(xin[t], s_w[t * O + g + k], acc[k]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaxf(acc[k], 0.f);
-        tfy_st16(y + (idx * 8), TfyPack<__nv_bfloat16>::pack(acc));
+            for (int k = 0; k < 8; ++k) acc[k] = fmaxf(acc[k], 0.f);
+            tfy_st16(yp + g, TfyPack<__nv_bfloat16>::pack(acc));
+        }
     }
 }
 
-// dW[o][t] = sum over (b,oh,ow) x[b,oh+kh,ow+kw] * dz[b,oh,ow,o].  blockDim = 9*O threads
-// (thread -> (tap, o)); each CTA reduces a contiguous chunk of output pixels, partials are merged
-// by the last CTA and stored as bf16 [O][9].
+// dW[o][t] = sum over (b,oh,ow) x[b,oh+kh,ow+kw] * dz[b,oh,ow,o].
+// lane <-> output channel (O == 32 fast path; general O loops channel blocks of 32); each warp walks a
+// strip of output pixels: one coalesced 64-byte dz load and nine warp-broadcast x loads per pixel, nine
+// FMAs per lane.  Warps are combined in shared memory, CTAs through `partial` + the last-CTA finalise.
 template <typename XT>
-__global__ void tfy_conv3x3_c1_wgrad_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
-                                            float* __restrict__ partial, __nv_bfloat16* __restrict__ dw,
-                                            uint32_t* counter, int B, int H, int W, int O) {
+__global__ void __launch_bounds__(256)
+tfy_conv3x3_c1_wgrad_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                            float* __restrict__ partial, __nv_bfloat16* __restrict__ dw, uint32_t* counter, int B,
+                            int H, int W, int O) {
+    extern __shared__ float s_acc[];   // [9*O] CTA accumulator, then reused as finalise scratch (>= blockDim)
     const int OH = H - 2, OW = W - 2;
-    const int t = threadIdx.x / O, o = threadIdx.x % O;
-    const int kh = t / 3, kw = t % 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 9 * O; i += blockDim.x) s_acc[i] = 0.f;
+    __syncthreads();
     const size_t npix = (size_t)B * OH * OW;
-    const size_t per = (npix + gridDim.x - 1) / gridDim.x;
-    const size_t p0 = per * blockIdx.x, p1 = min(npix, p0 + per);
-    float acc = 0.f;
-    for (size_t p = p0; p < p1; ++p) {
-        const int ow = p % OW;
-        const size_t r = p / OW;
-        const int oh = r % OH;
-        const int b = r / OH;
-        const float xv = (float)x[((size_t)b * H + oh + kh) * W + ow + kw];
-        acc = fmaf(xv, bf16_to_f(dz[p * O + o]), acc);
+    const size_t gw = (size_t)blockIdx.x * nwarps + warp, tw = (size_t)gridDim.x * nwarps;
+    for (int o0 = 0; o0 < O; o0 += 32) {
+        const int o = o0 + lane;
+        float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (size_t p = gw; p < npix; p += tw) {
+            const int ow = p % OW;
+            const size_t r = p / OW;
+            const int oh = r % OH;
+            const int b = r / OH;
+            const float d = (o < O) ? bf16_to_f(dz[p * O + o]) : 0.f;
+            const XT* xp = x + ((size_t)b * H + oh) * W + ow;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) acc[kh * 3 + kw] = fmaf((float)xp[kh * W + kw], d, acc[kh * 3 + kw]);
+        }
+        if (o < O) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) atomicAdd(&s_acc[o * 9 + t], acc[t]);
+        }
     }
-    // partial layout [grid][O*9] in (o, tap) order == the [O][9] weight layout
-    partial[(size_t)blockIdx.x * (9 * O) + o * 9 + t] = acc;
-    tfy_finalize_colsum(partial, 9 * O, dw, counter);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * O; i += blockDim.x) partial[(size_t)blockIdx.x * (9 * O) + i] = s_acc[i];
+    __syncthreads();
+    tfy_finalize_colsum(partial, 9 * O, dw, counter, s_acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -209,13 +267,9 @@ tfy_act_drop_bwd_bias_kernel(const __nv_bfloat16* dy, const uint8_t* __restrict_
         }
     }
     if (dbias) {
-        if (active) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[g * 8 + k], colacc[k]);
-        }
+        tfy_block_colsum(colacc, g, G, active, s_sum, C, partial + (size_t)blockIdx.x * C);
         __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) partial[(size_t)blockIdx.x * C + c] = s_sum[c];
-        tfy_finalize_colsum(partial, C, dbias, counter);
+        tfy_finalize_colsum(partial, C, dbias, counter, s_sum);
     }
 }
 
@@ -321,13 +375,9 @@ tfy_pool_drop_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dp, const uint8_
         }
     }
     if (dbias) {
-        if (active) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[g * 8 + k], colacc[k]);
-        }
+        tfy_block_colsum(colacc, g, G, active, s_sum, C, partial + (size_t)blockIdx.x * C);
         __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) partial[(size_t)blockIdx.x * C + c] = s_sum[c];
-        tfy_finalize_colsum(partial, C, dbias, counter);
+        tfy_finalize_colsum(partial, C, dbias, counter, s_sum);
     }
 }
 
@@ -341,38 +391,62 @@ tfy_softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfl
                         const long long* __restrict__ labels, float* __restrict__ loss,
                         __nv_bfloat16* __restrict__ dlogits, __nv_bfloat16* __restrict__ dbias,
                         float* __restrict__ stats, int B, int C) {
-    extern __shared__ float sm[];  // [C] dbias accumulators + [2] loss, correct
-    float* s_db = sm;
-    float* s_red = sm + C;
-    for (int c = threadIdx.x; c < C + 2; c += blockDim.x) sm[c] = 0.f;
+    extern __shared__ float sm[];  // [C] bias | [C] dbias accumulators | [2] loss, correct
+    float* s_bias = sm;
+    float* s_db = sm + C;
+    float* s_red = sm + 2 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        s_bias[c] = bias ? bf16_to_f(bias[c]) : 0.f;
+        s_db[c] = 0.f;
+    }
+    if (threadIdx.x < 2) s_red[threadIdx.x] = 0.f;
     __syncthreads();
     const float invB = 1.f / (float)B;
+    const int lane = threadIdx.x & 31;
     float my_loss = 0.f, my_correct = 0.f;
-    for (int r = threadIdx.x; r < B; r += blockDim.x) {
-        const __nv_bfloat16* row = logits + (size_t)r * C;
+    // every warp iterates the same number of times so that the shuffles below stay convergent
+    const int rounds = (B + blockDim.x - 1) / blockDim.x;
+    for (int it = 0; it < rounds; ++it) {
+        const int r = it * blockDim.x + threadIdx.x;
+        const bool ok = r < B;
+        const __nv_bfloat16* row = logits + (size_t)(ok ? r : 0) * C;
         float mx = -3.0e38f;
         int amax = 0;
         for (int c = 0; c < C; ++c) {
-            const float v = bf16_to_f(row[c]) + (bias ? bf16_to_f(bias[c]) : 0.f);
+            const float v = bf16_to_f(row[c]) + s_bias[c];
             if (v > mx) { mx = v; amax = c; }
         }
         float se = 0.f;
-        for (int c = 0; c < C; ++c) se += __expf(bf16_to_f(row[c]) + (bias ? bf16_to_f(bias[c]) : 0.f) - mx);
+        for (int c = 0; c < C; ++c) se += __expf(bf16_to_f(row[c]) + s_bias[c] - mx);
         const float lse = mx + __logf(se);
-        const int lab = (int)labels[r];
+        const int lab = ok ? (int)labels[r] : 0;
         const float inv_se = 1.f / se;
         for (int c = 0; c < C; ++c) {
-            const float v = bf16_to_f(row[c]) + (bias ? bf16_to_f(bias[c]) : 0.f);
-            const float prob = __expf(v - mx) * inv_se;
-            const float d = (prob - (c == lab ? 1.f : 0.f)) * invB;
-            if (c == lab) my_loss += lse - v;
-            dlogits[(size_t)r * C + c] = __float2bfloat16(d);
-            if (dbias) atomicAdd(&s_db[c], d);
+            const float v = bf16_to_f(row[c]) + s_bias[c];
+            float d = (__expf(v - mx) * inv_se - (c == lab ? 1.f : 0.f)) * invB;
+            if (!ok) d = 0.f;
+            if (ok) {
+                if (c == lab) my_loss += lse - v;
+                dlogits[(size_t)r * C + c] = __float2bfloat16(d);
+            }
+            if (dbias) {
+                float t = d;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+                if (lane == 0) atomicAdd(&s_db[c], t);
+            }
         }
-        my_correct += (amax == lab) ? 1.f : 0.f;
+        if (ok) my_correct += (amax == lab) ? 1.f : 0.f;
     }
-    atomicAdd(&s_red[0], my_loss);
-    atomicAdd(&s_red[1], my_correct);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        my_loss += __shfl_xor_sync(0xffffffffu, my_loss, off);
+        my_correct += __shfl_xor_sync(0xffffffffu, my_correct, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_red[0], my_loss);
+        atomicAdd(&s_red[1], my_correct);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         *loss = s_red[0] * invB;
@@ -400,7 +474,7 @@ size_t tfy_nn_max_partial_blocks() { return 592; }
 int tfy_conv3x3_c1_fwd(const void* x, int x_is_f32, const void* w, const void* bias, void* y, int B, int H, int W,
                        int O, cudaStream_t s) {
     if (O % 8) return -2;
-    const size_t total = (size_t)B * (H - 2) * (W - 2) * (O / 8);
+    const size_t total = (size_t)B * (H - 2) * (W - 2);
     const int grid = tfy_grid_for(total, 256, 148 * 8);
     const size_t smem = (size_t)(10 * O) * sizeof(float);
     if (x_is_f32)
@@ -415,13 +489,13 @@ int tfy_conv3x3_c1_fwd(const void* x, int x_is_f32, const void* w, const void* b
 
 int tfy_conv3x3_c1_wgrad(const void* x, int x_is_f32, const void* dz, float* partial, void* dw, uint32_t* counter,
                          int B, int H, int W, int O, cudaStream_t s) {
-    if (9 * O > 1024) return -2;
-    const int grid = 592;
+    const int grid = 296;
+    const size_t smem = (size_t)(9 * O > 256 ? 9 * O : 256) * sizeof(float);
     if (x_is_f32)
-        tfy_conv3x3_c1_wgrad_kernel<float><<<grid, 9 * O, 0, s>>>((const float*)x, (const __nv_bfloat16*)dz, partial,
-                                                                   (__nv_bfloat16*)dw, counter, B, H, W, O);
+        tfy_conv3x3_c1_wgrad_kernel<float><<<grid, 256, smem, s>>>((const float*)x, (const __nv_bfloat16*)dz, partial,
+                                                                    (__nv_bfloat16*)dw, counter, B, H, W, O);
     else
-        tfy_conv3x3_c1_wgrad_kernel<__nv_bfloat16><<<grid, 9 * O, 0, s>>>(
+        tfy_conv3x3_c1_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, partial, (__nv_bfloat16*)dw, counter, B, H, W, O);
     return (int)cudaGetLastError();
 }
@@ -439,10 +513,10 @@ int tfy_bias_act_drop_fwd(const void* z, const void* bias, void* y, void* mask, 
 int tfy_act_drop_bwd_bias(const void* dy, const void* mask, const void* y, void* dz, float scale, size_t rows, int C,
                           float* partial, void* dbias, uint32_t* counter, cudaStream_t s) {
     if (C % 8) return -2;
-    int grid = tfy_grid_for(rows * (C / 8), 256, 592);
+    int grid = tfy_grid_for(rows * (C / 8), 256 * 4, 296);
     // the kernel needs gridDim*blockDim >= C/8 so that every column group has a thread
     if ((size_t)grid * 256 < (size_t)(C / 8)) grid = (C / 8 + 255) / 256;
-    tfy_act_drop_bwd_bias_kernel<<<grid, 256, C * sizeof(float), s>>>(
+    tfy_act_drop_bwd_bias_kernel<<<grid, 256, (C > 256 ? C : 256) * sizeof(float), s>>>(
         (const __nv_bfloat16*)dy, (const uint8_t*)mask, (const __nv_bfloat16*)y, (__nv_bfloat16*)dz, scale, rows, C,
         partial, (__nv_bfloat16*)dbias, counter);
     return (int)cudaGetLastError();
@@ -463,8 +537,8 @@ int tfy_pool_drop_relu_bwd(const void* dp, const void* code, void* dz, float sca
                            float* partial, void* dbias, uint32_t* counter, cudaStream_t s) {
     if (C % 8 || H % 2 || W % 2) return -2;
     const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-    int grid = tfy_grid_for(total, 256, 592);
-    tfy_pool_drop_relu_bwd_kernel<<<grid, 256, C * sizeof(float), s>>>(
+    int grid = tfy_grid_for(total, 256 * 2, 296);
+    tfy_pool_drop_relu_bwd_kernel<<<grid, 256, (C > 256 ? C : 256) * sizeof(float), s>>>(
         (const __nv_bfloat16*)dp, (const uint8_t*)code, (__nv_bfloat16*)dz, scale, B, H, W, C, partial,
         (__nv_bfloat16*)dbias, counter);
     return (int)cudaGetLastError();
@@ -474,7 +548,7 @@ int tfy_softmax_xent(const void* logits, const void* bias, const void* labels, f
                      void* dbias, float* stats, int B, int C, cudaStream_t s) {
     int block = B < 1024 ? ((B + 31) / 32) * 32 : 1024;
     if (block < 32) block = 32;
-    tfy_softmax_xent_kernel<<<1, block, (C + 2) * sizeof(float), s>>>(
+    tfy_softmax_xent_kernel<<<1, block, (2 * C + 2) * sizeof(float), s>>>(
         (const __nv_bfloat16*)logits, (const __nv_bfloat16*)bias, (const long long*)labels, loss,
         (__nv_bfloat16*)dlogits, (__nv_bfloat16*)dbias, stats, B, C);
     return (int)cudaGetLastError();
