@@ -214,9 +214,19 @@ class GraphTrainEngine:
                 self._forward_backward(self._static_x, self._static_y)
         self.stream.synchronize()
         if self.use_graph:
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=self.stream):
-                self._forward_backward(self._static_x, self._static_y)
+            # a CUDAGraph of an older engine being garbage-collected while this stream captures would
+            # invalidate the capture (cudaGraphExecDestroy is not allowed then): collect now, pause GC
+            import gc
+            gc.collect()
+            was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=self.stream):
+                    self._forward_backward(self._static_x, self._static_y)
+            finally:
+                if was_enabled:
+                    gc.enable()
         # undo the warm-up steps: training starts from the user's initial state
         with torch.cuda.stream(self.stream):
             fused.master.copy_(snap[0]); fused.s1.copy_(snap[1]); fused.s2.copy_(snap[2])

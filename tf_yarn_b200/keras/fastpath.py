@@ -23,12 +23,14 @@ import torch.nn.functional as F
 
 from tf_yarn_b200.keras import layers as L
 from tf_yarn_b200.keras.engine import GraphTrainEngine
+from tf_yarn_b200.ops import gemm as _gemm  # noqa: F401  (declares tfy_gemm_bf16)
 from tf_yarn_b200.ops import native
 
 _vp, _i, _sz, _f, _u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_uint32
 native.declare("tfy_conv3x3_c1_fwd", [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c1_wgrad", [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
 native.declare("tfy_bias_act_drop_fwd", [_vp, _vp, _vp, _vp, _sz, _i, _i, _f, _u32, _vp, _vp])
+native.declare("tfy_bias_act_drop_fwd_f32", [_vp, _vp, _vp, _vp, _sz, _i, _i, _f, _u32, _vp, _vp])
 native.declare("tfy_act_drop_bwd_bias", [_vp, _vp, _vp, _vp, _f, _sz, _i, _vp, _vp, _vp, _vp])
 native.declare("tfy_bias_relu_pool_drop_fwd", [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u32, _vp, _vp])
 native.declare("tfy_pool_drop_relu_bwd", [_vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp])
@@ -134,6 +136,7 @@ class FastSequentialEngine(GraphTrainEngine):
         self._seed = int(torch.initial_seed() & 0x7fffffff)
         self._hp = self.fused.hyper.data_ptr()
         self._k = 0
+        self._acc32 = {}
 
     # ------------------------------------------------------------------ helpers
     def _s(self):
@@ -147,6 +150,20 @@ class FastSequentialEngine(GraphTrainEngine):
     def _wb(self, layer):
         mod = layer.module
         return mod.weight, mod.bias
+
+    @staticmethod
+    def _split_k(M: int, N: int, K: int) -> int:
+        """Split factor of the tcgen05 GEMM for skinny-output / long-K dense layers (1 = use cuBLAS)."""
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        k_tiles = (K + 63) // 64
+        if K % 8 or tiles > 8 or k_tiles < 32:
+            return 1
+        return max(1, min(k_tiles // 3, 48 // tiles))
+
+    def _splitk_acc(self, key, M: int, N: int) -> torch.Tensor:
+        if key not in self._acc32:
+            self._acc32[key] = torch.zeros((M, N), dtype=torch.float32, device=self.device)
+        return self._acc32[key]
 
     def pop_metrics(self):
         self.stream.synchronize()
@@ -232,13 +249,28 @@ class FastSequentialEngine(GraphTrainEngine):
                 ly = st.layer
                 w, b = self._wb(ly)
                 xin = cur.to(bf16) if cur.dtype != bf16 else cur
-                z = torch.mm(xin, w.t())
                 mask = torch.empty((B, ly.units), dtype=torch.uint8, device=cur.device) \
                     if (st.drop > 0 or st.relu) else None
-                self._chk(lib.tfy_bias_act_drop_fwd(z.data_ptr(), b.data_ptr(), z.data_ptr(),
-                                                    mask.data_ptr() if mask is not None else None, B, ly.units,
-                                                    int(st.relu), float(st.drop), seed, self._hp, s),
-                          "bias_act_drop_fwd")
+                K = xin.shape[1]
+                split = self._split_k(B, ly.units, K)
+                if split > 1:
+                    # skinny GEMM with a long K (e.g. 128 x 128 x 9216): split K over ~48 CTAs of the
+                    # tcgen05 kernel; partial sums meet in an fp32 accumulator that the epilogue clears
+                    acc = self._splitk_acc(li, B, ly.units)
+                    self._chk(lib.tfy_gemm_bf16(xin.data_ptr(), w.data_ptr(), None, acc.data_ptr(), None, B,
+                                                ly.units, K, xin.stride(0), w.stride(0), ly.units, 0, split, s),
+                              "gemm_bf16(split-K)")
+                    z = torch.empty((B, ly.units), dtype=bf16, device=cur.device)
+                    self._chk(lib.tfy_bias_act_drop_fwd_f32(acc.data_ptr(), b.data_ptr(), z.data_ptr(),
+                                                            mask.data_ptr() if mask is not None else None, B,
+                                                            ly.units, int(st.relu), float(st.drop), seed, self._hp,
+                                                            s), "bias_act_drop_fwd_f32")
+                else:
+                    z = torch.mm(xin, w.t())
+                    self._chk(lib.tfy_bias_act_drop_fwd(z.data_ptr(), b.data_ptr(), z.data_ptr(),
+                                                        mask.data_ptr() if mask is not None else None, B, ly.units,
+                                                        int(st.relu), float(st.drop), seed, self._hp, s),
+                              "bias_act_drop_fwd")
                 saved.append((xin, mask))
                 cur = z
                 cur_is_f32 = False

@@ -35,13 +35,13 @@ __device__ __forceinline__ float tfy_uniform(uint32_t seed, uint32_t step, uint6
 
 __device__ __forceinline__ float bf16_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// Last-CTA finalisation of per-CTA partial column sums: partial[gridDim.x][C] fp32 -> out[C] bf16.
-// `counter` must be zero on entry and is reset to zero by the finishing CTA (replay safe).
-// The finishing CTA sums in parallel: thread (r, c) accumulates the CTAs b = r, r+R, ... of column c,
-// then the R partial results per column are combined through shared memory (`scratch`, >= blockDim floats).
-__device__ void tfy_finalize_colsum(const float* partial, int C, __nv_bfloat16* out, uint32_t* counter,
-                                    float* scratch) {
+// Cross-CTA column sums without a serial tail: every CTA adds its C block sums (in shared memory)
+// into a global fp32 accumulator with RED; the CTA that arrives last swaps each accumulator with
+// zero (atomicExch), which both reads the total and re-arms the buffer for the next launch / graph
+// replay, and stores the bf16 result.  `gacc` (>= C floats) and `counter` must be zero on entry.
+__device__ void tfy_colsum_publish(const float* s_sum, int C, float* gacc, __nv_bfloat16* out, uint32_t* counter) {
     __shared__ bool is_last;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&gacc[c], s_sum[c]);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -51,31 +51,14 @@ __device__ void tfy_finalize_colsum(const float* partial, int C, __nv_bfloat16* 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const int nthr = blockDim.x;
-    for (int c0 = 0; c0 < C; c0 += nthr) {
-        const int cols = min(C - c0, nthr);
-        const int R = nthr / cols;                      // row-slices working on this column chunk
-        const int r = threadIdx.x / cols, c = threadIdx.x % cols;
-        float s = 0.f;
-        if (r < R)
-            for (unsigned b = r; b < gridDim.x; b += R) s += __ldcg(partial + (size_t)b * C + c0 + c);
-        __syncthreads();
-        scratch[threadIdx.x] = (r < R) ? s : 0.f;
-        __syncthreads();
-        if (threadIdx.x < cols) {
-            float t = 0.f;
-            for (int rr = 0; rr < R; ++rr) t += scratch[rr * cols + threadIdx.x];
-            out[c0 + threadIdx.x] = __float2bfloat16(t);
-        }
-    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) out[c] = __float2bfloat16(atomicExch(&gacc[c], 0.f));
     if (threadIdx.x == 0) *counter = 0;
 }
 
 // Per-CTA column sums of values held 8-per-thread (column group g of G = C/8): reduce the lanes of a
 // warp that share a group with shuffles, combine the warps through shared memory (s_sum: [C] floats,
 // zeroed by the caller before use), then publish this CTA's row of `partial`.
-__device__ __forceinline__ void tfy_block_colsum(float (&colacc)[8], int g, int G, bool active, float* s_sum, int C,
-                                                 float* partial_row) {
+__device__ __forceinline__ void tfy_block_colsum(float (&colacc)[8], int g, int G, bool active, float* s_sum) {
     if (G < 32 && (32 % G) == 0 && (blockDim.x % 32) == 0) {
         // lanes l and l + k*G of a warp hold the same column group (the grid stride keeps g = tid % G)
 #pragma unroll
@@ -93,7 +76,6 @@ __device__ __forceinline__ void tfy_block_colsum(float (&colacc)[8], int g, int 
         for (int k = 0; k < 8; ++k) atomicAdd(&s_sum[g * 8 + k], colacc[k]);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) partial_row[c] = s_sum[c];
 }
 
 }  // namespace
@@ -155,7 +137,7 @@ __global__ void __launch_bounds__(256)
 tfy_conv3x3_c1_wgrad_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                             float* __restrict__ partial, __nv_bfloat16* __restrict__ dw, uint32_t* counter, int B,
                             int H, int W, int O) {
-    extern __shared__ float s_acc[];   // [9*O] CTA accumulator, then reused as finalise scratch (>= blockDim)
+    extern __shared__ float s_acc[];   // [9*O] CTA accumulator
     const int OH = H - 2, OW = W - 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 9 * O; i += blockDim.x) s_acc[i] = 0.f;
@@ -165,17 +147,33 @@ tfy_conv3x3_c1_wgrad_kernel(const XT* __restrict__ x, const __nv_bfloat16* __res
     for (int o0 = 0; o0 < O; o0 += 32) {
         const int o = o0 + lane;
         float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (size_t p = gw; p < npix; p += tw) {
-            const int ow = p % OW;
-            const size_t r = p / OW;
-            const int oh = r % OH;
-            const int b = r / OH;
-            const float d = (o < O) ? bf16_to_f(dz[p * O + o]) : 0.f;
-            const XT* xp = x + ((size_t)b * H + oh) * W + ow;
+        // 4 pixels per trip: all loads of the trip are issued before the FMAs consume them
+        for (size_t p0 = gw; p0 < npix; p0 += 4 * tw) {
+            float d[4];
+            const XT* xp[4];
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
+            for (int u = 0; u < 4; ++u) {
+                const size_t p = p0 + (size_t)u * tw;
+                const bool ok = p < npix;
+                const size_t pc = ok ? p : 0;
+                const int ow = pc % OW;
+                const size_t r = pc / OW;
+                const int oh = r % OH;
+                const int b = r / OH;
+                d[u] = (ok && o < O) ? bf16_to_f(dz[pc * O + o]) : 0.f;
+                xp[u] = x + ((size_t)b * H + oh) * W + ow;
+            }
+            float xv[4][9];
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) acc[kh * 3 + kw] = fmaf((float)xp[kh * W + kw], d, acc[kh * 3 + kw]);
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) xv[u][kh * 3 + kw] = (float)xp[u][kh * W + kw];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc[t] = fmaf(xv[u][t], d[u], acc[t]);
         }
         if (o < O) {
 #pragma unroll
@@ -183,17 +181,18 @@ tfy_conv3x3_c1_wgrad_kernel(const XT* __restrict__ x, const __nv_bfloat16* __res
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 9 * O; i += blockDim.x) partial[(size_t)blockIdx.x * (9 * O) + i] = s_acc[i];
-    __syncthreads();
-    tfy_finalize_colsum(partial, 9 * O, dw, counter, s_acc);
+    tfy_colsum_publish(s_acc, 9 * O, partial, dw, counter);
 }
 
 // ---------------------------------------------------------------------------------------------
 // y = dropout(act(z + bias[c])) over a [rows, C] bf16 matrix (C % 8 == 0); y may alias z.
 // mask (optional, 1 byte per element): 1 = gradient flows (act'(.) != 0 and kept).
 // ---------------------------------------------------------------------------------------------
+// ZT = __nv_bfloat16: z is a bf16 matrix.  ZT = float: z is the fp32 split-K accumulator of the tcgen05
+// GEMM; it is consumed AND cleared here so the next step's partial sums start from zero.
+template <typename ZT>
 __global__ void __launch_bounds__(256)
-tfy_bias_act_drop_fwd_kernel(const __nv_bfloat16* z, const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* y,
+tfy_bias_act_drop_fwd_kernel(ZT* z, const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* y,
                              uint8_t* __restrict__ mask, size_t rows, int C, int relu, float drop_rate, uint32_t seed,
                              const TfyOptHyper* __restrict__ hp) {
     const int G = C / 8;
@@ -204,7 +203,15 @@ tfy_bias_act_drop_fwd_kernel(const __nv_bfloat16* z, const __nv_bfloat16* __rest
          idx += (size_t)gridDim.x * blockDim.x) {
         const int g = idx % G;
         float v[8], bv[8];
-        TfyPack<__nv_bfloat16>::unpack(tfy_ld16(z + idx * 8), v);
+        if (sizeof(ZT) == 4) {
+            float4* zp = reinterpret_cast<float4*>(z) + idx * 2;
+            const float4 a = zp[0], b = zp[1];
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            zp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+            zp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            TfyPack<__nv_bfloat16>::unpack(tfy_ld16(reinterpret_cast<const __nv_bfloat16*>(z) + idx * 8), v);
+        }
         if (bias) {
             TfyPack<__nv_bfloat16>::unpack(tfy_ld16(bias + g * 8), bv);
 #pragma unroll
@@ -267,9 +274,8 @@ tfy_act_drop_bwd_bias_kernel(const __nv_bfloat16* dy, const uint8_t* __restrict_
         }
     }
     if (dbias) {
-        tfy_block_colsum(colacc, g, G, active, s_sum, C, partial + (size_t)blockIdx.x * C);
-        __syncthreads();
-        tfy_finalize_colsum(partial, C, dbias, counter, s_sum);
+        tfy_block_colsum(colacc, g, G, active, s_sum);
+        tfy_colsum_publish(s_sum, C, partial, dbias, counter);
     }
 }
 
@@ -375,9 +381,8 @@ tfy_pool_drop_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dp, const uint8_
         }
     }
     if (dbias) {
-        tfy_block_colsum(colacc, g, G, active, s_sum, C, partial + (size_t)blockIdx.x * C);
-        __syncthreads();
-        tfy_finalize_colsum(partial, C, dbias, counter, s_sum);
+        tfy_block_colsum(colacc, g, G, active, s_sum);
+        tfy_colsum_publish(s_sum, C, partial, dbias, counter);
     }
 }
 
@@ -504,9 +509,20 @@ int tfy_bias_act_drop_fwd(const void* z, const void* bias, void* y, void* mask, 
                           float drop_rate, uint32_t seed, const TfyOptHyper* hp, cudaStream_t s) {
     if (C % 8) return -2;
     const int grid = tfy_grid_for(rows * (C / 8), 256, 148 * 8);
-    tfy_bias_act_drop_fwd_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)z, (const __nv_bfloat16*)bias,
-                                                      (__nv_bfloat16*)y, (uint8_t*)mask, rows, C, relu, drop_rate,
-                                                      seed, hp);
+    tfy_bias_act_drop_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)z, (const __nv_bfloat16*)bias,
+                                                                     (__nv_bfloat16*)y, (uint8_t*)mask, rows, C, relu,
+                                                                     drop_rate, seed, hp);
+    return (int)cudaGetLastError();
+}
+
+// same, reading (and clearing) the fp32 split-K accumulator z32 [rows, C]
+int tfy_bias_act_drop_fwd_f32(void* z32, const void* bias, void* y, void* mask, size_t rows, int C, int relu,
+                              float drop_rate, uint32_t seed, const TfyOptHyper* hp, cudaStream_t s) {
+    if (C % 8) return -2;
+    const int grid = tfy_grid_for(rows * (C / 8), 256, 148 * 8);
+    tfy_bias_act_drop_fwd_kernel<float><<<grid, 256, 0, s>>>((float*)z32, (const __nv_bfloat16*)bias,
+                                                             (__nv_bfloat16*)y, (uint8_t*)mask, rows, C, relu,
+                                                             drop_rate, seed, hp);
     return (int)cudaGetLastError();
 }
 
