@@ -42,7 +42,7 @@ def test_xset_environ(monkeypatch):
     with pytest.raises(RuntimeError):
         xset_environ(TFY_TEST_FOO="baz")
     assert os.environ["TFY_TEST_FOO"] == "bar"
-    monkeypatch.delenv("TFY_TEST_FOO")
+    os.environ.pop("TFY_TEST_FOO", None)
 
 
 def test_iter_tasks():

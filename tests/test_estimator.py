@@ -1,0 +1,156 @@
+"""mini-Estimator on CPU: train/evaluate/predict, checkpoints, hooks, continuous eval, exporters."""
+import os
+
+import pytest
+import torch
+
+from tf_yarn_b200 import data, keras
+from tf_yarn_b200 import estimator as est
+from tf_yarn_b200.estimator import checkpoint as ckpt
+
+fc = est.feature_column
+
+
+def _data(n=1024, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 6, generator=g)
+    w = torch.randn(6, 3, generator=g)
+    return x, (x @ w).argmax(1)
+
+
+def _input_fns():
+    x, y = _data()
+    train = lambda: data.Dataset.from_tensor_slices(({"x": x}, y)).shuffle(500, seed=1).batch(64).repeat()  # noqa: E731
+    evalf = lambda: data.Dataset.from_tensor_slices(({"x": x}, y)).batch(256)  # noqa: E731
+    return train, evalf
+
+
+def _classifier(model_dir, **cfg):
+    return est.LinearClassifier([fc.numeric_column("x", shape=(6,))], model_dir=str(model_dir), n_classes=3,
+                                optimizer=lambda: keras.optimizers.Adam(0.05),
+                                config=est.RunConfig(save_checkpoints_steps=50, log_step_count_steps=None, **cfg))
+
+
+def test_train_evaluate_predict_and_checkpoint_index(tmp_path):
+    train, evalf = _input_fns()
+    e = _classifier(tmp_path)
+    e.train(train, max_steps=120)
+    state = est.get_checkpoint_state(str(tmp_path))
+    assert [ckpt.step_of(p) for p in state.all_model_checkpoint_paths] == [0, 50, 100, 120]
+    assert est.latest_checkpoint(str(tmp_path)).endswith("model.ckpt-120")
+    res = e.evaluate(evalf)
+    assert res["global_step"] == 120 and res["accuracy"] > 0.85
+    first = next(iter(e.predict(evalf)))
+    assert set(first) == {"logits", "probabilities", "class_ids"}
+    # evaluation of an older checkpoint reports that checkpoint's step
+    old = e.evaluate(evalf, checkpoint_path=state.all_model_checkpoint_paths[1], name="old")
+    assert old["global_step"] == 50
+    assert os.path.isdir(tmp_path / "eval_old")
+
+
+def test_training_resumes_from_latest_checkpoint(tmp_path):
+    train, _ = _input_fns()
+    _classifier(tmp_path).train(train, max_steps=60)
+    e2 = _classifier(tmp_path)
+    e2.train(train, max_steps=100)
+    assert e2.get_global_step() == 100
+    e3 = _classifier(tmp_path)
+    e3.train(train, max_steps=100)           # already there: no further step
+    assert e3.get_global_step() == 100
+
+
+def test_hooks_receive_global_step_and_can_stop(tmp_path):
+    train, _ = _input_fns()
+    seen = []
+
+    class Spy(est.SessionRunHook):
+        def before_run(self, ctx):
+            return est.SessionRunArgs(est.get_global_step())
+
+        def after_run(self, ctx, values):
+            seen.append(values.results)
+    e = _classifier(tmp_path)
+    e.train(train, hooks=[Spy(), est.StopAtStepHook(last_step=7)], max_steps=1000)
+    assert seen == list(range(1, 8)) and e.get_global_step() == 7
+
+
+def test_step_counter_hook_reports_rate():
+    hook = est.StepCounterHook(every_n_steps=2)
+    ctx = est.SessionRunContext()
+    for step in range(1, 6):
+        hook.after_run(ctx, est.SessionRunValues(results=step))
+    assert hook.last_steps_per_sec is not None and hook.last_steps_per_sec > 0
+    with pytest.raises(ValueError):
+        est.StepCounterHook(every_n_steps=None, every_n_secs=None)
+
+
+def test_train_and_evaluate_local_with_exporter(tmp_path, monkeypatch):
+    monkeypatch.delenv("TF_CONFIG", raising=False)
+    train, evalf = _input_fns()
+    e = _classifier(tmp_path)
+    res, _ = est.train_and_evaluate(e, est.TrainSpec(train, max_steps=80),
+                                    est.EvalSpec(evalf, steps=None, exporters=est.FinalExporter("final")))
+    assert res["global_step"] == 80
+    exports = os.listdir(tmp_path / "export" / "final")
+    assert len(exports) == 1 and os.path.exists(tmp_path / "export" / "final" / exports[0] / "saved_model.pt")
+
+
+def test_continuous_eval_evaluates_only_new_checkpoints_and_stops_at_max_steps(tmp_path):
+    train, evalf = _input_fns()
+    e = _classifier(tmp_path)
+    e.train(train, max_steps=100)
+    evaluated = []
+
+    class Rec(est.Exporter):
+        def export(self, estimator, export_path, checkpoint_path, eval_result, is_final):
+            evaluated.append((ckpt.step_of(checkpoint_path), is_final))
+    res = est.continuous_eval(e, est.TrainSpec(train, max_steps=100),
+                              est.EvalSpec(evalf, steps=2, exporters=[Rec("rec")], start_delay_secs=0, throttle_secs=0),
+                              timeout_secs=30, evaluated_steps={0})
+    assert [s for s, _ in evaluated] == [50, 100] and evaluated[-1][1] is True
+    assert res["global_step"] == 100
+
+
+def test_dnn_and_wide_deep_estimators_learn(tmp_path):
+    g = torch.Generator().manual_seed(3)
+    n = 1024
+    num = torch.randn(n, 4, generator=g)
+    cat = torch.randint(0, 50, (n, 1), generator=g)
+    y = ((num[:, 0] > 0) ^ (cat[:, 0] % 2 == 0)).long()
+    feats = {"num": num, "cat": cat}
+    train = lambda: data.Dataset.from_tensor_slices((feats, y)).shuffle(500, seed=0).batch(64).repeat()  # noqa: E731
+    evalf = lambda: data.Dataset.from_tensor_slices((feats, y)).batch(256)  # noqa: E731
+    cat_col = fc.categorical_column_with_identity("cat", 50)
+    e = est.DNNLinearCombinedClassifier(
+        model_dir=str(tmp_path), linear_feature_columns=[cat_col],
+        dnn_feature_columns=[fc.numeric_column("num", shape=(4,)), fc.embedding_column(cat_col, 8)],
+        dnn_hidden_units=[32, 16], dnn_optimizer=lambda: keras.optimizers.Adam(0.01),
+        config=est.RunConfig(save_checkpoints_steps=None, save_checkpoints_secs=None, log_step_count_steps=None))
+    e.train(train, max_steps=400)
+    assert e.evaluate(evalf)["accuracy"] > 0.85
+
+
+def test_model_to_estimator(tmp_path):
+    x, y = _data()
+    m = keras.Sequential([keras.layers.Dense(16, activation="relu", input_shape=(6,)), keras.layers.Dense(3)])
+    m.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True), optimizer=keras.optimizers.Adam(0.02),
+              metrics=["accuracy"])
+    e = est.model_to_estimator(m, model_dir=str(tmp_path),
+                               config=est.RunConfig(save_checkpoints_steps=None, save_checkpoints_secs=None,
+                                                    log_step_count_steps=None))
+    train = lambda: data.Dataset.from_tensor_slices(({"features": x}, y)).batch(64).repeat()  # noqa: E731
+    e.train(train, max_steps=200)
+    assert e.evaluate(lambda: data.Dataset.from_tensor_slices(({"features": x}, y)).batch(256))["accuracy"] > 0.8
+
+
+def test_run_config_replace_and_cluster_info(monkeypatch):
+    cfg = est.RunConfig(model_dir="/m", session_config=est.SessionConfig(device_filters=["/job:ps"]))
+    assert cfg.replace(model_dir=None, save_summary_steps=None).model_dir is None and cfg.model_dir == "/m"
+    with pytest.raises(ValueError):
+        cfg.replace(nope=1)
+    monkeypatch.setenv("TF_CONFIG", '{"cluster": {"chief": ["a:1"], "worker": ["b:2", "c:3"], "ps": ["d:4"]}, '
+                                    '"task": {"type": "worker", "index": 1}}')
+    info = est.ClusterInfo.from_env()
+    assert (info.task_type, info.task_id, info.has_ps, info.is_chief) == ("worker", 1, True, False)
+    assert info.trainers() == ["chief:0", "worker:0", "worker:1"]
+    assert cfg.num_ps_replicas == 1 and cfg.num_worker_replicas == 3

@@ -38,7 +38,7 @@ def test_setup_tf_config(monkeypatch):
     assert cfg["task"] == {"type": "worker", "index": 1} and cfg["environment"] == "google"
     with pytest.raises(RuntimeError):          # exclusive set: never overwrite an existing TF_CONFIG
         cluster.setup_tf_config({"chief": ["a:1"]})
-    monkeypatch.delenv("TF_CONFIG")
+    os.environ.pop("TF_CONFIG", None)      # set behind monkeypatch's back by xset_environ
 
 
 @pytest.mark.parametrize("task,started", [("worker:0", True), ("chief:0", True), ("ps:0", False),
