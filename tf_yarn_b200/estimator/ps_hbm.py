@@ -141,7 +141,8 @@ class HbmConnection:
             if isinstance(mod, nn.EmbeddingBag) and id(mod.weight) in by_param and mod.embedding_dim % 4 == 0 \
                     and mod.mode in ("sum", "mean"):
                 self.sparse[by_param[id(mod.weight)]] = mod
-            elif isinstance(mod, nn.Linear) and id(mod.weight) in by_param and mod.in_features % 8 == 0:
+            elif isinstance(mod, nn.Linear) and id(mod.weight) in by_param and mod.in_features % 8 == 0 \
+                    and mod.out_features >= 8:
                 self.gemm[by_param[id(mod.weight)]] = mod
 
     def _make_segs(self, for_push: bool):

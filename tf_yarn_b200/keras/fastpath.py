@@ -158,7 +158,7 @@ class FastSequentialEngine(GraphTrainEngine):
         k_tiles = (K + 63) // 64
         if K % 8 or tiles > 8 or k_tiles < 32:
             return 1
-        return max(1, min(k_tiles // 3, 48 // tiles))
+        return max(1, min(k_tiles // 6, 24 // tiles))      # 6 k-tiles per CTA == the TMA ring depth
 
     def _splitk_acc(self, key, M: int, N: int) -> torch.Tensor:
         if key not in self._acc32:

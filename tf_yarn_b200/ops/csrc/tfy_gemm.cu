@@ -194,9 +194,18 @@ tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
             if (out_mode == 1) {
                 float* dst = C32 + (size_t)row * ldc + n;
+                if (n + 16 <= N && (ldc & 3) == 0 && (n & 3) == 0) {
+                    // 4 x red.v4.f32 instead of 16 scalar REDs
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n + j < N) atomicAdd(dst + j, v[j]);
+                    for (int j = 0; j < 16; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(v[j]),
+                                     "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                                     : "memory");
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n + j < N) atomicAdd(dst + j, v[j]);
+                }
             } else {
                 if (bias) {
 #pragma unroll

@@ -36,12 +36,16 @@ __device__ __forceinline__ float tfy_uniform(uint32_t seed, uint32_t step, uint6
 __device__ __forceinline__ float bf16_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // Cross-CTA column sums without a serial tail: every CTA adds its C block sums (in shared memory)
-// into a global fp32 accumulator with RED; the CTA that arrives last swaps each accumulator with
-// zero (atomicExch), which both reads the total and re-arms the buffer for the next launch / graph
-// replay, and stores the bf16 result.  `gacc` (>= C floats) and `counter` must be zero on entry.
+// into one of TFY_ACC_GROUPS global fp32 accumulator rows with RED (spreading the CTAs over several rows
+// keeps the same-address contention at the L2 atomic units low); the CTA that arrives last swaps every
+// accumulator with zero (atomicExch) -- which reads the totals AND re-arms the buffer for the next
+// launch / graph replay -- and stores the bf16 result.  `gacc` (>= TFY_ACC_GROUPS*C floats) and
+// `counter` must be zero on entry.
+#define TFY_ACC_GROUPS 16
 __device__ void tfy_colsum_publish(const float* s_sum, int C, float* gacc, __nv_bfloat16* out, uint32_t* counter) {
     __shared__ bool is_last;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&gacc[c], s_sum[c]);
+    float* row = gacc + (size_t)(blockIdx.x % TFY_ACC_GROUPS) * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&row[c], s_sum[c]);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -51,7 +55,12 @@ __device__ void tfy_colsum_publish(const float* s_sum, int C, float* gacc, __nv_
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) out[c] = __float2bfloat16(atomicExch(&gacc[c], 0.f));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < TFY_ACC_GROUPS; ++g) t += atomicExch(&gacc[(size_t)g * C + c], 0.f);
+        out[c] = __float2bfloat16(t);
+    }
     if (threadIdx.x == 0) *counter = 0;
 }
 
@@ -529,7 +538,7 @@ int tfy_bias_act_drop_fwd_f32(void* z32, const void* bias, void* y, void* mask, 
 int tfy_act_drop_bwd_bias(const void* dy, const void* mask, const void* y, void* dz, float scale, size_t rows, int C,
                           float* partial, void* dbias, uint32_t* counter, cudaStream_t s) {
     if (C % 8) return -2;
-    int grid = tfy_grid_for(rows * (C / 8), 256 * 4, 296);
+    int grid = tfy_grid_for(rows * (C / 8), 256, 296);
     // the kernel needs gridDim*blockDim >= C/8 so that every column group has a thread
     if ((size_t)grid * 256 < (size_t)(C / 8)) grid = (C / 8 + 255) / 256;
     tfy_act_drop_bwd_bias_kernel<<<grid, 256, (C > 256 ? C : 256) * sizeof(float), s>>>(
