@@ -117,8 +117,17 @@ def test_fast_path_plan_grammar():
     m.build()
     kinds = [s.kind for s in fastpath.build_plan(m)]
     assert kinds == ["conv", "conv", "flatten", "dense", "head"]
-    # softmax output (probabilities) is outside the fused grammar -> autograd engine
+    # softmax output + probability loss is the same fused head
     m2 = keras_mnist_cnn(logits=False)
     m2.compile(loss="sparse_categorical_crossentropy", optimizer="adadelta")
     m2.build()
-    assert fastpath.build_plan(m2) is None
+    assert [s.kind for s in fastpath.build_plan(m2)][-1] == "head"
+    # mismatched head (softmax layer feeding a from_logits loss) or another loss: autograd engine
+    m3 = keras_mnist_cnn(logits=False)
+    m3.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True), optimizer="adadelta")
+    m3.build()
+    assert fastpath.build_plan(m3) is None
+    m4 = keras_mnist_cnn()
+    m4.compile(loss="mse", optimizer="adadelta")
+    m4.build()
+    assert fastpath.build_plan(m4) is None

@@ -51,7 +51,13 @@ def build_plan(model) -> Optional[List[_Stage]]:
     """Pattern-match the layer list; None if the model is outside the fast-path grammar."""
     from tf_yarn_b200.keras import losses as kl
     loss = model.loss
-    if not (isinstance(loss, kl.SparseCategoricalCrossentropy) and loss.from_logits):
+    # the fused head computes softmax + cross-entropy from logits: either the loss takes logits and the
+    # last layer is linear, or the last layer is a softmax and the loss takes probabilities
+    if isinstance(loss, kl.SparseCategoricalCrossentropy):
+        want_head_activation = "linear" if loss.from_logits else "softmax"
+    elif loss == "sparse_categorical_crossentropy":
+        want_head_activation = "softmax"
+    else:
         return None
     for m in model._metrics_spec:
         if m not in ("accuracy", "acc", "sparse_categorical_accuracy"):
@@ -86,11 +92,12 @@ def build_plan(model) -> Optional[List[_Stage]]:
             plan.append(_Stage("flatten"))
             i += 1
         elif isinstance(ly, L.Dense):
-            if not ly.use_bias or ly.activation_name not in ("relu", "linear"):
+            last = i + 1 >= n
+            if not ly.use_bias or ly.activation_name not in (("relu", "linear") if not last
+                                                             else (want_head_activation,)):
                 return None
-            last = all(isinstance(x, L.Dropout) for x in layers[i + 1:]) and i + 1 >= n
             if last:
-                if ly.activation_name != "linear":
+                if ly.units > 1024:
                     return None
                 plan.append(_Stage("head", layer=ly))
                 i += 1
