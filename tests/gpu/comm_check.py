@@ -248,6 +248,7 @@ def main():
                     P[o:o + nn] = t.reshape(-1)
                 S1 = torch.full_like(P, spec.init_s1)
                 S2 = torch.zeros_like(P)
+                _, scratch_g = arena.empty((fo.n,), gdt)
                 ok = True
                 worst = 0.0
                 for step in range(4):
@@ -259,7 +260,15 @@ def main():
                     torch.cuda.synchronize()
                     G = sum(x.float() for x in grads_all)
                     if gdt == torch.bfloat16 and comm.mode == native.MODE_NVLS:
-                        G = G.to(torch.bfloat16).float()  # the switch rounds the fp32 sum to bf16 once
+                        # the NVSwitch returns the bf16 sum with its own rounding (not round-to-nearest):
+                        # take the reference gradient from the plain NVLS all-reduce kernel (validated
+                        # above against the exact sum) so the optimizer math is compared bit-for-bit
+                        scratch_g.copy_(grads_all[rank])
+                        torch.cuda.synchronize()
+                        dist.barrier()
+                        G = comm.all_reduce_symm(scratch_g, average=False, algo=native.ALGO_NVLS).float().clone()
+                        torch.cuda.synchronize()
+                        dist.barrier()
                     G = G / world
                     P, S1, S2 = ref_optimizer(kind, P, G, S1, S2, hp, step)
                     got = fo.flat_params.float()
