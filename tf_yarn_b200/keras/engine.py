@@ -186,7 +186,7 @@ class GraphTrainEngine:
     # ------------------------------------------------------------------ step body
     def _forward_backward(self, x, y) -> None:
         xin = x
-        if torch.is_floating_point(xin):
+        if torch.is_tensor(xin) and torch.is_floating_point(xin):
             xin = xin.to(self.compute_dtype)
         out = self.net(xin)
         loss = self.loss_fn(y, out)

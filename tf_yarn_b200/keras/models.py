@@ -164,6 +164,8 @@ class Model:
         if not self.layers:
             raise ValueError("model has no layers")
         shape = input_shape if input_shape is not None else self.layers[0]._declared_input_shape
+        if shape is None and isinstance(self.layers[0], L.TorchModule):
+            shape = ()               # wrapped torch modules (possibly with dict inputs) carry their own shapes
         if shape is None:
             raise ValueError("the first layer needs input_shape=... (or call build(input_shape) / fit on data)")
         shape = tuple(shape)

@@ -360,8 +360,10 @@ int tfy_fused_step(const TfyCommCtx* c, int grad_dtype, int param_dtype, int opt
                    int zero_grads, int grid, int block, cudaStream_t s) {
     if (shard_n % 8) return -2;
     if (mode == TFY_MODE_NVLS && c->mc_base == 0) return -5;
-    if (block <= 0) block = 256;
-    if (grid <= 0) grid = tfy_pick_grid(shard_n / 8, block, 148 * 2);
+    if (block <= 0) block = (mode == TFY_MODE_LOCAL) ? 128 : 256;
+    // single GPU: nothing to synchronise with, so oversubscribe the SMs for memory-level parallelism;
+    // multi GPU: every CTA runs two cross-GPU barriers, keep one wave
+    if (grid <= 0) grid = tfy_pick_grid(shard_n / 8, block, mode == TFY_MODE_LOCAL ? 148 * 6 : 148 * 2);
     if (grid > TFY_MAX_BLOCKS) grid = TFY_MAX_BLOCKS;
 #define TFY_FS4(GT, PT, O, M)                                                                                  \
     tfy_fused_step_kernel<GT, PT, O, M><<<grid, block, 0, s>>>(*c, grad_off, param_off, shard_n, master, s1, s2, \

@@ -138,9 +138,10 @@ tfy_conv3x3_c1_fwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restr
 }
 
 // dW[o][t] = sum over (b,oh,ow) x[b,oh+kh,ow+kw] * dz[b,oh,ow,o].
-// lane <-> output channel (O == 32 fast path; general O loops channel blocks of 32); each warp walks a
-// strip of output pixels: one coalesced 64-byte dz load and nine warp-broadcast x loads per pixel, nine
-// FMAs per lane.  Warps are combined in shared memory, CTAs through `partial` + the last-CTA finalise.
+// lane <-> output channel (blocks of 32 channels).  A warp owns whole output rows (b, oh): it loads the
+// three input rows it needs ONCE (coalesced, lane = column; W <= 32 fast path) and walks ow with the
+// window values coming from warp shuffles -- per pixel one 64-byte dz load, 9 shuffles, 9 FMAs and no
+// integer division.  Warps are combined in shared memory, CTAs through tfy_colsum_publish.
 template <typename XT>
 __global__ void __launch_bounds__(256)
 tfy_conv3x3_c1_wgrad_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
@@ -151,40 +152,42 @@ tfy_conv3x3_c1_wgrad_kernel(const XT* __restrict__ x, const __nv_bfloat16* __res
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 9 * O; i += blockDim.x) s_acc[i] = 0.f;
     __syncthreads();
-    const size_t npix = (size_t)B * OH * OW;
-    const size_t gw = (size_t)blockIdx.x * nwarps + warp, tw = (size_t)gridDim.x * nwarps;
+    const int nrows = B * OH;
+    const int gw = blockIdx.x * nwarps + warp, tw = gridDim.x * nwarps;
     for (int o0 = 0; o0 < O; o0 += 32) {
         const int o = o0 + lane;
+        const bool o_ok = o < O;
         float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        // 4 pixels per trip: all loads of the trip are issued before the FMAs consume them
-        for (size_t p0 = gw; p0 < npix; p0 += 4 * tw) {
-            float d[4];
-            const XT* xp[4];
+        for (int row = gw; row < nrows; row += tw) {
+            const int b = row / OH, oh = row - b * OH;
+            const XT* xr = x + ((size_t)b * H + oh) * W;
+            const __nv_bfloat16* dzr = dz + (size_t)row * OW * O + o;
+            if (W <= 32) {
+                const float r0 = lane < W ? (float)xr[lane] : 0.f;
+                const float r1 = lane < W ? (float)xr[W + lane] : 0.f;
+                const float r2 = lane < W ? (float)xr[2 * W + lane] : 0.f;
+#pragma unroll 2
+                for (int ow = 0; ow < OW; ++ow) {
+                    const float d = o_ok ? bf16_to_f(dzr[(size_t)ow * O]) : 0.f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const size_t p = p0 + (size_t)u * tw;
-                const bool ok = p < npix;
-                const size_t pc = ok ? p : 0;
-                const int ow = pc % OW;
-                const size_t r = pc / OW;
-                const int oh = r % OH;
-                const int b = r / OH;
-                d[u] = (ok && o < O) ? bf16_to_f(dz[pc * O + o]) : 0.f;
-                xp[u] = x + ((size_t)b * H + oh) * W + ow;
+                    for (int kw = 0; kw < 3; ++kw) {
+                        acc[0 + kw] = fmaf(__shfl_sync(0xffffffffu, r0, ow + kw), d, acc[0 + kw]);
+                        acc[3 + kw] = fmaf(__shfl_sync(0xffffffffu, r1, ow + kw), d, acc[3 + kw]);
+                        acc[6 + kw] = fmaf(__shfl_sync(0xffffffffu, r2, ow + kw), d, acc[6 + kw]);
+                    }
+                }
+            } else {
+                for (int ow = 0; ow < OW; ++ow) {
+                    const float d = o_ok ? bf16_to_f(dzr[(size_t)ow * O]) : 0.f;
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw)
+                            acc[kh * 3 + kw] = fmaf((float)xr[kh * W + ow + kw], d, acc[kh * 3 + kw]);
+                }
             }
-            float xv[4][9];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) xv[u][kh * 3 + kw] = (float)xp[u][kh * W + kw];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                for (int t = 0; t < 9; ++t) acc[t] = fmaf(xv[u][t], d[u], acc[t]);
         }
-        if (o < O) {
+        if (o_ok) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) atomicAdd(&s_acc[o * 9 + t], acc[t]);
         }
@@ -538,7 +541,7 @@ int tfy_bias_act_drop_fwd_f32(void* z32, const void* bias, void* y, void* mask, 
 int tfy_act_drop_bwd_bias(const void* dy, const void* mask, const void* y, void* dz, float scale, size_t rows, int C,
                           float* partial, void* dbias, uint32_t* counter, cudaStream_t s) {
     if (C % 8) return -2;
-    int grid = tfy_grid_for(rows * (C / 8), 256, 296);
+    int grid = tfy_grid_for(rows * (C / 8), 256, 592);
     // the kernel needs gridDim*blockDim >= C/8 so that every column group has a thread
     if ((size_t)grid * 256 < (size_t)(C / 8)) grid = (C / 8 + 255) / 256;
     tfy_act_drop_bwd_bias_kernel<<<grid, 256, (C > 256 ? C : 256) * sizeof(float), s>>>(
@@ -562,7 +565,7 @@ int tfy_pool_drop_relu_bwd(const void* dp, const void* code, void* dz, float sca
                            float* partial, void* dbias, uint32_t* counter, cudaStream_t s) {
     if (C % 8 || H % 2 || W % 2) return -2;
     const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-    int grid = tfy_grid_for(total, 256 * 2, 296);
+    int grid = tfy_grid_for(total, 256, 592);
     tfy_pool_drop_relu_bwd_kernel<<<grid, 256, (C > 256 ? C : 256) * sizeof(float), s>>>(
         (const __nv_bfloat16*)dp, (const uint8_t*)code, (__nv_bfloat16*)dz, scale, B, H, W, C, partial,
         (__nv_bfloat16*)dbias, counter);

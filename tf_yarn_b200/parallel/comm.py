@@ -185,19 +185,54 @@ class Communicator:
         return t
 
     def broadcast(self, tensors: Sequence[torch.Tensor], root: int = 0, stream=None) -> None:
-        """Broadcast arbitrary CUDA tensors from ``root`` through the fusion buffer."""
+        """Broadcast arbitrary CUDA tensors from ``root``: packed into the fusion buffer (one multi-tensor
+        copy), ONE broadcast kernel per fusion-buffer fill, unpacked (tensors larger than the buffer go
+        through it in pieces)."""
+        if self.world == 1 or not tensors:
+            return
+        batch: List[torch.Tensor] = []
+        used = 0
+
+        def flush():
+            nonlocal batch, used
+            if not batch:
+                return
+            views = []
+            o = 0
+            for t in batch:
+                nb = t.numel() * t.element_size()
+                views.append(self._fusion_u8[o:o + nb].view(t.dtype).view(t.shape))
+                o += (nb + 15) // 16 * 16
+            if self.rank == root:
+                torch._foreach_copy_(views, batch)
+            self.broadcast_symm(self._fusion_u8[:o], root, stream)
+            if self.rank != root:
+                torch._foreach_copy_(batch, views)
+            batch, used = [], 0
+
         for t in tensors:
-            flat = t.contiguous().view(-1).view(torch.uint8)
-            n = flat.numel()
-            for s in range(0, n, self.fusion_bytes):
-                piece = flat[s:s + self.fusion_bytes]
-                padded = (piece.numel() + 15) // 16 * 16
-                buf = self._fusion_u8[:padded]
-                buf[:piece.numel()].copy_(piece)
-                self.broadcast_symm(buf, root, stream)
-                piece.copy_(buf[:piece.numel()])
-            if not t.is_contiguous():
-                t.copy_(flat.view(t.dtype).view(t.shape))
+            nb = t.numel() * t.element_size()
+            if nb > self.fusion_bytes or not t.is_contiguous():
+                flush()
+                flat = t.contiguous().view(-1).view(torch.uint8)
+                for s in range(0, flat.numel(), self.fusion_bytes):
+                    piece = flat[s:s + self.fusion_bytes]
+                    padded = (piece.numel() + 15) // 16 * 16
+                    buf = self._fusion_u8[:padded]
+                    if self.rank == root:
+                        buf[:piece.numel()].copy_(piece)
+                    self.broadcast_symm(buf, root, stream)
+                    if self.rank != root:
+                        piece.copy_(buf[:piece.numel()])
+                if not t.is_contiguous() and self.rank != root:
+                    t.copy_(flat.view(t.dtype).view(t.shape))
+                continue
+            padded = (nb + 15) // 16 * 16
+            if used + padded > self.fusion_bytes:
+                flush()
+            batch.append(t)
+            used += padded
+        flush()
 
     def all_gather_symm(self, t: torch.Tensor, stream=None) -> torch.Tensor:
         """``t`` is [world * shard] in the arena; rank r's slice r is valid on entry."""
