@@ -1,0 +1,73 @@
+"""Host-side logic of the DDP-like wrapper (bucketing, grad views, hooks) with a single-rank fake communicator."""
+import torch
+import torch.nn as nn
+
+from tf_yarn_b200.parallel.ddp import DistributedDataParallel
+
+
+class _FakeArena:
+    def empty(self, shape, dtype, align=256):
+        return 0, torch.zeros(shape, dtype=dtype)
+
+
+class _FakeComm:
+    world, rank, device = 1, 0, 0
+    arena = _FakeArena()
+
+    def pad_elems(self, n, dtype):
+        return (n + 7) // 8 * 8
+
+
+def _model():
+    torch.manual_seed(0)
+    return nn.Sequential(nn.Linear(300, 700), nn.ReLU(), nn.Linear(700, 600), nn.ReLU(), nn.Linear(600, 10))
+
+
+def test_buckets_are_built_in_reverse_order_with_a_small_first_bucket():
+    ddp = DistributedDataParallel(_model(), _FakeComm(), bucket_cap_mb=1)
+    sizes = [sum(p.numel() * 4 for p in b.params) for b in ddp._buckets]
+    assert len(ddp._buckets) >= 2
+    assert sizes[0] <= 1 << 20 or len(ddp._buckets[0].params) == 1
+    first_params = ddp._buckets[0].params
+    last_layer = list(ddp.module.parameters())[-1]
+    assert first_params[0] is last_layer                    # reverse registration order
+
+
+def test_gradients_land_in_bucket_views_and_match_plain_backward():
+    model, ref = _model(), _model()
+    ddp = DistributedDataParallel(model, _FakeComm(), bucket_cap_mb=1)
+    x = torch.randn(16, 300)
+    ddp(x).sum().backward()
+    ref(x).sum().backward()
+    for p, r in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, r.grad, atol=1e-6)
+        b, i = ddp._param_bucket[id(p)]
+        assert p.grad.data_ptr() == b.flat[b.offsets[i]:].data_ptr()       # a view into the flat bucket
+    assert all(b.pending == len(b.params) and not b.launched for b in ddp._buckets)   # reset after backward
+
+
+def test_zero_grad_set_to_none_is_recovered_and_no_sync_accumulates():
+    model = _model()
+    ddp = DistributedDataParallel(model, _FakeComm(), bucket_cap_mb=1)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    x = torch.randn(8, 300)
+    ddp(x).sum().backward()
+    g1 = [p.grad.clone() for p in model.parameters()]
+    opt.zero_grad(set_to_none=True)                       # user code drops the views ...
+    ddp(x).sum().backward()                               # ... the hook folds the fresh grads back into them
+    for p, g in zip(model.parameters(), g1):
+        b, i = ddp._param_bucket[id(p)]
+        assert p.grad.data_ptr() == b.flat[b.offsets[i]:].data_ptr()
+        assert torch.allclose(p.grad, g, atol=1e-6)
+    ddp.zero_grad()
+    with ddp.no_sync():
+        ddp(x).sum().backward()
+    ddp(x).sum().backward()
+    for p, g in zip(model.parameters(), g1):
+        assert torch.allclose(p.grad, 2 * g, atol=1e-5)
+
+
+def test_state_dict_is_the_inner_modules():
+    model = _model()
+    ddp = DistributedDataParallel(model, _FakeComm())
+    assert ddp.state_dict().keys() == model.state_dict().keys()

@@ -337,6 +337,10 @@ def _execute_and_await_termination(
                     if "/logs" in key and key not in container_log_urls:
                         container_log_urls[key] = app.kv.wait(key).decode()
         if report.final_status != FinalStatus.UNDEFINED:
+            # last look at the side channels (a short job may end within one poll period)
+            with suppress(Exception):
+                eval_metrics_logger.log()
+                tensorboard_url_logger.log()
             # drain: give the aggregator a moment to receive the last PUTs, then stop it
             _join_listener(cluster.event_listener)
             log_events, result_metrics, container_status = _handle_events(cluster.events, n_try)
@@ -348,8 +352,9 @@ def _execute_and_await_termination(
             if report.final_status == FinalStatus.FAILED:
                 failed = [f"{k.to_kv_str()}: {s}" for k, s in container_status.container_status.items()
                           if s in ("FAILED", "KILLED")]
+                tails = _failed_log_tails(logs, container_status)
                 raise RunFailed(f"application {app.id} failed ({'; '.join(failed)}); logs in {app.log_dir}\n"
-                                + log_events)
+                                + log_events + tails)
             break
         eval_metrics_logger.log()
         tensorboard_url_logger.log()
@@ -357,6 +362,18 @@ def _execute_and_await_termination(
         state = report.state
     result_metrics.log_mlflow(n_try)
     return result_metrics
+
+
+def _failed_log_tails(logs: Optional[Dict[str, str]], status: "ContainerLogStatus", n_lines: int = 15) -> str:
+    """Last lines of the log of every task that died without publishing a ``stop`` event."""
+    if not logs:
+        return ""
+    out = []
+    for container_id, (task, st) in status.by_container_id().items():
+        if st == "KILLED" and logs.get(container_id):
+            tail = "\n".join(logs[container_id].rstrip().splitlines()[-n_lines:])
+            out.append(f"\n--- last lines of {task.to_kv_str()} ({container_id}):\n{tail}")
+    return "".join(out)
 
 
 def _join_listener(listener: threading.Thread, settle_secs: float = 0.3) -> None:

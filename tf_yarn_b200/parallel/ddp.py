@@ -56,10 +56,10 @@ class DistributedDataParallel(nn.Module):
         self.broadcast_buffers = broadcast_buffers
         self.find_unused_parameters = find_unused_parameters
         self.require_backward_grad_sync = True
-        self._comm_stream = torch.cuda.Stream(device=comm.device)
+        self._comm_stream = torch.cuda.Stream(device=comm.device) if comm.world > 1 else None
         self._callback_queued = False
         self._buckets: List[_Bucket] = []
-        self._param_bucket = {}
+        self._param_bucket = {}          # id(param) -> (bucket, index in bucket); tensors compare elementwise
         self._build_buckets(int(bucket_cap_mb) << 20)
         self._sync_params_and_buffers()
         for b in self._buckets:
@@ -91,9 +91,9 @@ class DistributedDataParallel(nn.Module):
             n = self.comm.pad_elems(n, b.dtype)
             _, b.flat = self.comm.arena.empty((n,), b.dtype, align=4096)
             b.flat.zero_()
-            for p, o in zip(b.params, b.offsets):
+            for i, (p, o) in enumerate(zip(b.params, b.offsets)):
                 p.grad = b.flat[o:o + p.numel()].view_as(p)
-                self._param_bucket[p] = b
+                self._param_bucket[id(p)] = (b, i)
             b.pending = len(b.params)
 
     def _sync_params_and_buffers(self) -> None:
@@ -104,14 +104,13 @@ class DistributedDataParallel(nn.Module):
         torch.cuda.current_stream().synchronize()
 
     def _grad_view(self, p: nn.Parameter) -> torch.Tensor:
-        b = self._param_bucket[p]
-        o = b.offsets[b.params.index(p)]
+        b, i = self._param_bucket[id(p)]
+        o = b.offsets[i]
         return b.flat[o:o + p.numel()].view_as(p)
 
     # ------------------------------------------------------------------ hooks
     def _make_hook(self, p: nn.Parameter):
-        bucket = self._param_bucket[p]
-        idx = bucket.params.index(p)
+        bucket, idx = self._param_bucket[id(p)]
         off = bucket.offsets[idx]
         view = bucket.flat[off:off + p.numel()].view_as(p)
 
@@ -150,7 +149,7 @@ class DistributedDataParallel(nn.Module):
             if not b.launched:
                 # parameters that received no gradient this step contribute zeros
                 self._launch(b)
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream() if self.comm.world > 1 else None
         for b in self._buckets:
             if b.event is not None:
                 cur.wait_event(b.event)

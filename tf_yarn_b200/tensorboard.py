@@ -30,7 +30,8 @@ def start_tf_board(client, tf_board_model_dir: str) -> Optional[str]:
     task = get_task()
     try:
         from tensorboard import program
-        program.setup_environment()
+        if hasattr(program, "setup_environment"):       # removed from recent TensorBoard releases
+            program.setup_environment()
         board = program.TensorBoard()
         with _internal.reserve_sock_addr() as (host, port):
             url = f"http://{host}:{port}"

@@ -26,7 +26,13 @@ def main() -> None:
         cluster.setup_tf_config(cluster_spec)
         experiment = _task_commons._get_experiment(client)
         if isinstance(experiment, KerasExperiment):
-            raise ValueError("KerasExperiment using parameter strategy is unsupported")
+            # the reference raises here without telling anybody (the task shows up as KILLED);
+            # publish the reason so the client's report carries it
+            err = ValueError("KerasExperiment using parameter strategy is unsupported")
+            from tf_yarn_b200 import event
+            event.start_event(client, _task_commons.get_task())
+            event.stop_event(client, _task_commons.get_task(), err)
+            raise err
         session_config = experiment.config.session_config
     cluster.start_tf_server(cluster_spec, session_config)
     thread = tf_task_common._execute_dispatched_function(client, experiment)
