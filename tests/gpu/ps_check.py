@@ -18,6 +18,7 @@ from tf_yarn_b200.tensorflow import Experiment, run_on_yarn  # noqa: E402
 
 model_dir = tempfile.mkdtemp(prefix="tfy_ps_gpu_")
 N_WORKERS = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+N_PS = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 MAX_STEPS = 300
 
 
@@ -37,7 +38,7 @@ def experiment_fn():
                       est.EvalSpec(eval_fn, steps=None, start_delay_secs=0, throttle_secs=1))
 
 
-specs = {"chief": TaskSpec("4 GiB", 4, label=NodeLabel.GPU), "ps": TaskSpec("4 GiB", 2, label=NodeLabel.GPU),
+specs = {"chief": TaskSpec("4 GiB", 4, label=NodeLabel.GPU), "ps": TaskSpec("4 GiB", 2, instances=N_PS, label=NodeLabel.GPU),
          "evaluator": TaskSpec("4 GiB", 2)}
 if N_WORKERS:
     specs["worker"] = TaskSpec("4 GiB", 4, instances=N_WORKERS, label=NodeLabel.GPU)
@@ -47,7 +48,8 @@ sc = summary.read_scalars(os.path.join(model_dir, "eval"))
 acc = [(s, v) for s, n, v in zip(sc["step"], sc["name"], sc["value"]) if n == "accuracy"]
 print("eval accuracy by step:", acc)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump({"accuracy": acc, "training_s": metrics.total_training_duration.total_seconds()},
-          open("gpurun_out/ps_check.json", "w"))
+json.dump({"accuracy": acc, "training_s": metrics.total_training_duration.total_seconds(), "workers": N_WORKERS,
+           "ps": N_PS, "max_steps": MAX_STEPS},
+          open(f"gpurun_out/ps_check_w{N_WORKERS}_ps{N_PS}.json", "w"))
 assert acc and acc[-1][1] > max(0.6, acc[0][1]), acc
 print("PS CHECK OK")
