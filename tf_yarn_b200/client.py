@@ -238,6 +238,7 @@ def run_on_yarn(
         if value:
             logger.debug("run_on_yarn(%s=...) has no meaning on a single box; ignored", ignored)
     interpreter = _setup_pyenvs(pyenv_zip_path)
+    files = _add_editable_requirements(files)
 
     n_try = 0
     while True:
@@ -261,6 +262,16 @@ def run_on_yarn(
 
 
 run_on_b200 = run_on_yarn
+
+
+def _add_editable_requirements(files: Optional[Dict[str, str]]) -> Dict[str, str]:
+    """The reference ships editable (``pip -e``) installs to the containers (client.py:498-505); on one
+    box they are importable already, so this only normalises ``files``."""
+    from tf_yarn_b200 import packaging
+    files = dict(files or {})
+    for dirname, path in packaging.get_editable_requirements().items():
+        files.setdefault(dirname, path)
+    return files
 
 
 def _setup_pyenvs(pyenv_zip_path: Union[str, Dict[topologies.NodeLabel, str], None]) -> Optional[str]:

@@ -192,6 +192,21 @@ def broadcast(tensor: torch.Tensor, root_rank: int = 0, name: Optional[str] = No
     return broadcast_(tensor.clone(), root_rank, name)
 
 
+def allgather(tensor: torch.Tensor, name: Optional[str] = None) -> torch.Tensor:
+    """Concatenate equally shaped tensors of all ranks along dim 0."""
+    _check()
+    if _state["size"] == 1:
+        return tensor.clone()
+    if _on_gpu(tensor):
+        flat = _communicator().all_gather(tensor.contiguous().view(-1))
+        return flat.view(_state["size"] * tensor.shape[0], *tensor.shape[1:])
+    import torch.distributed as dist
+    ensure_cpu_group()
+    out = [torch.empty_like(tensor) for _ in range(_state["size"])]
+    dist.all_gather(out, tensor)
+    return torch.cat(out, dim=0)
+
+
 def broadcast_parameters(params, root_rank: int = 0) -> None:
     """Broadcast a ``state_dict`` / iterable of (name, tensor) / iterable of tensors from ``root_rank``."""
     if isinstance(params, dict):
