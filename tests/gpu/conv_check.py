@@ -1,0 +1,153 @@
+"""tcgen05 implicit-GEMM convolution kernels (ops/csrc/tfy_conv.cu) against fp32 PyTorch references.
+
+Run on a B200: ``python tests/gpu/conv_check.py [B]``; writes gpurun_out/conv_check.json.
+"""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from tf_yarn_b200.keras import fastpath  # noqa: E402,F401  (declares the kernels)
+from tf_yarn_b200.ops import native  # noqa: E402
+
+lib = native.load()
+dev = torch.device("cuda:0")
+bf16 = torch.bfloat16
+res = {}
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def timeit(fn, reps=50):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1000.0 / reps
+
+
+def report(name, got, ref, tol):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-6
+    bad = err > tol * denom
+    ok = not bool(bad.any())
+    res[name] = {"ok": ok, "max_abs_err": err.max().item(), "ref_max": denom, "bad_frac": bad.float().mean().item()}
+    print(f"[{name}] ok={ok} max_err={err.max().item():.4g} ref_max={denom:.4g} bad={bad.float().mean().item():.4f}")
+    if not ok:
+        idx = bad.nonzero()[:6]
+        for i in idx:
+            t = tuple(i.tolist())
+            print("   at", t, "got", got[t].item(), "ref", ref[t].item())
+    return ok
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+    H = W = 26
+    torch.manual_seed(0)
+    a = torch.randn(B, H, W, 32, device=dev).relu().to(bf16)               # NHWC, like a ReLU output
+    w = (torch.randn(64, 3, 3, 32, device=dev) * 0.06).to(bf16)             # [O][kh][kw][C]
+    bias = (torch.randn(64, device=dev) * 0.1).to(bf16)
+    w_nchw = w.permute(0, 3, 1, 2).float()
+    a_nchw = a.permute(0, 3, 1, 2).float()
+
+    # ---------------------------------------------------------------- fprop (+bias, relu, pool)
+    pooled = torch.zeros(B, 12, 12, 64, dtype=bf16, device=dev)
+    code = torch.zeros(B, 12, 12, 64, dtype=torch.uint8, device=dev)
+    rc = lib.tfy_conv3x3_c32_pool_fwd(a.data_ptr(), w.data_ptr(), bias.data_ptr(), pooled.data_ptr(),
+                                      code.data_ptr(), B, H, W, 0.0, 1234, None, stream())
+    torch.cuda.synchronize()
+    print("fprop rc", rc)
+    z = F.conv2d(a_nchw, w_nchw)                                            # fp32 reference
+    zp, zi = F.max_pool2d(z, 2, return_indices=True)
+    ref = (zp + bias.float().view(1, -1, 1, 1)).relu().permute(0, 2, 3, 1)
+    report("fprop_pool", pooled, ref, 0.01)
+    # argmax code: position inside the window
+    zi = zi.permute(0, 2, 3, 1)
+    iy, ix = zi // 24, zi % 24
+    pos = (iy % 2) * 2 + (ix % 2)
+    agree = ((code & 3).long() == pos).float().mean().item()
+    on_ref = (ref > 0)
+    on_agree = (((code >> 2) & 1).bool() == on_ref).float().mean().item()
+    res["fprop_code"] = {"argmax_agree": agree, "gate_agree": on_agree, "ok": agree > 0.995 and on_agree > 0.995}
+    print(f"[fprop_code] argmax_agree={agree:.5f} gate_agree={on_agree:.5f}")
+    # dropout statistics + determinism of the mask for a given (seed, step)
+    hp = torch.zeros(16, dtype=torch.float32, device=dev)
+    p2 = torch.zeros_like(pooled)
+    c2 = torch.zeros_like(code)
+    lib.tfy_conv3x3_c32_pool_fwd(a.data_ptr(), w.data_ptr(), bias.data_ptr(), p2.data_ptr(), c2.data_ptr(), B, H, W,
+                                 0.25, 1234, hp.data_ptr(), stream())
+    torch.cuda.synchronize()
+    kept = ((p2 != 0) | (ref.to(bf16) == 0)).float().mean().item()
+    scale_ok = report("fprop_dropout_scale", torch.where(p2 != 0, p2.float() * 0.75, ref), ref, 0.01)
+    frac = 1.0 - ((p2 == 0) & (ref.to(bf16) != 0)).float().sum().item() / max(1.0, (ref.to(bf16) != 0).float().sum().item())
+    res["fprop_dropout"] = {"keep_frac": frac, "ok": abs(frac - 0.75) < 0.01 and scale_ok}
+    print(f"[fprop_dropout] keep_frac={frac:.4f} ({kept:.4f})")
+
+    # ---------------------------------------------------------------- dgrad
+    dz = (torch.randn(B, 24, 24, 64, device=dev) * 0.5).to(bf16)
+    dx = torch.full((B, H, W, 32), 7.0, dtype=bf16, device=dev)
+    rc = lib.tfy_conv3x3_c32_dgrad(dz.data_ptr(), w.data_ptr(), None, dx.data_ptr(), B, H, W, stream())
+    torch.cuda.synchronize()
+    print("dgrad rc", rc)
+    dx_ref = torch.nn.grad.conv2d_input((B, 32, H, W), w_nchw, dz.permute(0, 3, 1, 2).float()).permute(0, 2, 3, 1)
+    report("dgrad", dx, dx_ref, 0.01)
+    dxg = torch.zeros_like(dx)
+    lib.tfy_conv3x3_c32_dgrad(dz.data_ptr(), w.data_ptr(), a.data_ptr(), dxg.data_ptr(), B, H, W, stream())
+    torch.cuda.synchronize()
+    report("dgrad_gated", dxg, dx_ref * (a.float() > 0), 0.01)
+
+    # ---------------------------------------------------------------- wgrad
+    acc = torch.zeros(64 * 288, dtype=torch.float32, device=dev)
+    sync = torch.zeros(2, dtype=torch.int32, device=dev)
+    dw = torch.zeros(64, 3, 3, 32, dtype=bf16, device=dev)
+    dw_ref = torch.nn.grad.conv2d_weight(a_nchw, (64, 32, 3, 3), dz.permute(0, 3, 1, 2).float()).permute(0, 2, 3, 1)
+    for it in range(3):                      # repeated launches: accumulator re-zeroing and barrier reuse
+        rc = lib.tfy_conv3x3_c32_wgrad(a.data_ptr(), dz.data_ptr(), acc.data_ptr(), dw.data_ptr(), sync.data_ptr(),
+                                       B, H, W, stream())
+        torch.cuda.synchronize()
+        report(f"wgrad_{it}", dw, dw_ref, 0.01)
+    res["wgrad_acc_zero"] = {"ok": bool((acc == 0).all()), "sync": sync.tolist()}
+    print("wgrad rc", rc, "acc zero:", bool((acc == 0).all()), "sync", sync.tolist())
+
+    # ---------------------------------------------------------------- timings (hot L2; the in-graph numbers
+    # come from profiles/launches_*.csv)
+    t = {}
+    t["fprop_pool_tc_us"] = timeit(lambda: lib.tfy_conv3x3_c32_pool_fwd(
+        a.data_ptr(), w.data_ptr(), bias.data_ptr(), pooled.data_ptr(), code.data_ptr(), B, H, W, 0.25, 1234,
+        hp.data_ptr(), stream()))
+    t["dgrad_tc_us"] = timeit(lambda: lib.tfy_conv3x3_c32_dgrad(dz.data_ptr(), w.data_ptr(), a.data_ptr(),
+                                                                 dx.data_ptr(), B, H, W, stream()))
+    t["wgrad_tc_us"] = timeit(lambda: lib.tfy_conv3x3_c32_wgrad(a.data_ptr(), dz.data_ptr(), acc.data_ptr(),
+                                                                 dw.data_ptr(), sync.data_ptr(), B, H, W, stream()))
+    wcl = w.permute(0, 3, 1, 2)
+    acl = a.permute(0, 3, 1, 2)
+    dzcl = dz.permute(0, 3, 1, 2)
+    t["fprop_cudnn_us"] = timeit(lambda: F.conv2d(acl, wcl))
+    t["bwd_cudnn_us"] = timeit(lambda: torch.ops.aten.convolution_backward(
+        dzcl, acl, wcl, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, True, False]))
+    res["timings"] = t
+    print(json.dumps(t))
+    ok = all(v.get("ok", True) for v in res.values() if isinstance(v, dict))
+    res["all_ok"] = ok
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/conv_check.json", "w") as f:
+        json.dump(res, f, indent=1)
+    print("CONV CHECK", "PASS" if ok else "FAIL")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

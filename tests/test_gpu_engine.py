@@ -259,3 +259,18 @@ def test_tcgen05_gemm_matches_fp32_reference(shape):
         torch.cuda.synchronize()
         assert out3.dtype == torch.float32
         assert (out3 - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("batch", [2, 16])
+def test_tcgen05_conv_kernels_match_fp32_reference(batch, monkeypatch, tmp_path):
+    """Implicit-GEMM conv fprop(+bias/relu/pool/dropout), dgrad(+gate), wgrad vs fp32 PyTorch references."""
+    import importlib.util
+    import os
+    import sys
+    spec = importlib.util.spec_from_file_location(
+        "conv_check", os.path.join(os.path.dirname(__file__), "gpu", "conv_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "argv", ["conv_check.py", str(batch)])
+    assert mod.main() == 0, mod.res

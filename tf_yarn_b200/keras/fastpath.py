@@ -16,6 +16,7 @@ use the autograd engine (:class:`GraphTrainEngine`).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional
 
 import torch
@@ -35,6 +36,9 @@ native.declare("tfy_act_drop_bwd_bias", [_vp, _vp, _vp, _vp, _f, _sz, _i, _vp, _
 native.declare("tfy_bias_relu_pool_drop_fwd", [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _u32, _vp, _vp])
 native.declare("tfy_pool_drop_relu_bwd", [_vp, _vp, _vp, _f, _i, _i, _i, _i, _vp, _vp, _vp, _vp])
 native.declare("tfy_softmax_xent", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp])
+native.declare("tfy_conv3x3_c32_pool_fwd", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _u32, _vp, _vp])
+native.declare("tfy_conv3x3_c32_dgrad", [_vp, _vp, _vp, _vp, _i, _i, _i, _vp])
+native.declare("tfy_conv3x3_c32_wgrad", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 
 PARTIAL_BLOCKS = 592
 
@@ -144,6 +148,7 @@ class FastSequentialEngine(GraphTrainEngine):
         self._hp = self.fused.hyper.data_ptr()
         self._k = 0
         self._acc32 = {}
+        self._conv_sync = torch.zeros(2, dtype=torch.int32, device=dev)     # grid barrier of the wgrad kernel
 
     # ------------------------------------------------------------------ helpers
     def _s(self):
@@ -166,6 +171,16 @@ class FastSequentialEngine(GraphTrainEngine):
         if K % 8 or tiles > 8 or k_tiles < 32:
             return 1
         return max(1, min(k_tiles // 6, 24 // tiles))      # 6 k-tiles per CTA == the TMA ring depth
+
+    @staticmethod
+    def _tc_conv(st, B: int) -> bool:
+        """True when the stage is served by the tcgen05 implicit-GEMM kernels of ops/csrc/tfy_conv.cu."""
+        if os.environ.get("TFY_NO_TC_CONV") == "1":       # A/B switch: cuDNN + separate pool kernel instead
+            return False
+        ly = st.layer
+        H, W, Cin = ly.input_shape_
+        return (Cin == 32 and ly.filters == 64 and st.pool and st.relu and (H - 2) % 8 == 0 and (W - 2) % 8 == 0
+                and B % 2 == 0)
 
     def _splitk_acc(self, key, M: int, N: int) -> torch.Tensor:
         if key not in self._acc32:
@@ -206,6 +221,18 @@ class FastSequentialEngine(GraphTrainEngine):
                 O = ly.filters
                 OH, OW = H - 2, W - 2
                 fused_pre = False
+                if self._tc_conv(st, B):
+                    # tcgen05 implicit GEMM; bias + ReLU + 2x2 max-pool + dropout in the epilogue
+                    xin = cur if (cur.dtype == bf16 and cur.is_contiguous()) else cur.to(bf16).contiguous()
+                    p = torch.empty((B, OH // 2, OW // 2, O), dtype=bf16, device=cur.device)
+                    code = torch.empty((B, OH // 2, OW // 2, O), dtype=torch.uint8, device=cur.device)
+                    self._chk(lib.tfy_conv3x3_c32_pool_fwd(xin.data_ptr(), w.data_ptr(), b.data_ptr(), p.data_ptr(),
+                                                           code.data_ptr(), B, H, W, float(st.drop), seed, self._hp,
+                                                           s), "conv3x3_c32_pool_fwd")
+                    saved.append((xin, False, None, code))
+                    cur = p
+                    cur_is_f32 = False
+                    continue
                 if Cin == 1:
                     # direct kernel: conv + bias + relu in one launch (relu folded only when requested)
                     a = torch.empty((B, OH, OW, O), dtype=bf16, device=cur.device)
@@ -295,6 +322,7 @@ class FastSequentialEngine(GraphTrainEngine):
                 saved.append((xin, dlogits))
         # -------- backward
         grad = None
+        pre_gated = False          # the dgrad kernel of the next layer already applied this layer's ReLU gate
         for li in range(len(self.plan) - 1, -1, -1):
             st = self.plan[li]
             sv = saved[li]
@@ -326,6 +354,7 @@ class FastSequentialEngine(GraphTrainEngine):
                 O = ly.filters
                 OH, OW = H - 2, W - 2
                 scale = 1.0 / (1.0 - st.drop) if st.drop > 0 else 1.0
+                gated, pre_gated = pre_gated, False
                 if st.pool:
                     dz = torch.empty((B, OH, OW, O), dtype=bf16, device=grad.device)
                     self._chk(lib.tfy_pool_drop_relu_bwd(grad.data_ptr(), aux.data_ptr(), dz.data_ptr(), scale, B, OH,
@@ -335,7 +364,8 @@ class FastSequentialEngine(GraphTrainEngine):
                     dz = grad if grad.is_contiguous() else grad.contiguous()
                     use_mask = aux is not None
                     self._chk(lib.tfy_act_drop_bwd_bias(dz.data_ptr(), aux.data_ptr() if use_mask else None,
-                                                        zout.data_ptr() if (st.relu and not use_mask) else None,
+                                                        zout.data_ptr() if (st.relu and not use_mask
+                                                                            and not gated) else None,
                                                         dz.data_ptr(), scale, B * OH * OW, O,
                                                         self._partial.data_ptr(), b.grad.data_ptr(),
                                                         self._counter.data_ptr(), s), "act_drop_bwd_bias")
@@ -346,6 +376,23 @@ class FastSequentialEngine(GraphTrainEngine):
                     grad = None
                     if not first:
                         raise RuntimeError("C_in=1 convolution must be the first layer")
+                elif self._tc_conv(st, B):
+                    acc = self._splitk_acc(("wgrad", li), O, 9 * Cin)
+                    self._chk(lib.tfy_conv3x3_c32_wgrad(xin.data_ptr(), dz.data_ptr(), acc.data_ptr(),
+                                                        w.grad.data_ptr(), self._conv_sync.data_ptr(), B, H, W, s),
+                              "conv3x3_c32_wgrad")
+                    grad = None
+                    if not first:
+                        prev = self.plan[li - 1]
+                        # fold the producer's ReLU gate into the dgrad epilogue when its output IS our input
+                        fold = (prev.kind == "conv" and prev.relu and not prev.pool and prev.drop == 0
+                                and saved[li - 1][2] is not None and saved[li - 1][2].data_ptr() == xin.data_ptr())
+                        grad = torch.empty((B, H, W, Cin), dtype=bf16, device=dz.device)
+                        self._chk(lib.tfy_conv3x3_c32_dgrad(dz.data_ptr(), w.data_ptr(),
+                                                            xin.data_ptr() if fold else None, grad.data_ptr(), B, H,
+                                                            W, s), "conv3x3_c32_dgrad")
+                        pre_gated = fold
+                    continue
                 else:
                     xb = xin.to(bf16) if xin.dtype != bf16 else xin
                     dx, dw, _ = torch.ops.aten.convolution_backward(
