@@ -276,7 +276,9 @@ def main():
                     denom = expect.abs().clamp_min(1e-3)
                     rel = ((got - expect).abs() / denom).max().item()
                     worst = max(worst, rel)
-                    tol = 2e-2 if pdt == torch.bfloat16 else 2e-4
+                    # fp32: the in-switch summation order of `world` addends is not the reference's; Adadelta's
+                    # rsqrt amplifies the last-bit differences
+                    tol = 2e-2 if pdt == torch.bfloat16 else 2e-4 * max(1, world // 2)
                     if gdt == torch.bfloat16 and comm.mode != native.MODE_NVLS:
                         tol = max(tol, 2e-2)
                     # the replicated compute params must be exactly the (gathered) fp32 master cast down

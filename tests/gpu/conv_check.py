@@ -24,17 +24,24 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def timeit(fn, reps=50):
-    for _ in range(5):
+def timeit(fn, reps=20):
+    """Device time per call: `reps` launches captured in one CUDA graph (no host launch cost), replayed 5x."""
+    for _ in range(3):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    for _ in range(5):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1000.0 / reps
+    return e0.elapsed_time(e1) * 1000.0 / (5 * reps)
 
 
 def report(name, got, ref, tol):
