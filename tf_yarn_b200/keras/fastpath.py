@@ -39,6 +39,7 @@ native.declare("tfy_softmax_xent", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _
 native.declare("tfy_conv3x3_c32_pool_fwd", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _u32, _vp, _vp])
 native.declare("tfy_conv3x3_c32_dgrad", [_vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
+native.declare("tfy_conv3x3_c32_wgrad_scratch_elems", [], restype=ctypes.c_size_t)
 
 PARTIAL_BLOCKS = 592
 
@@ -377,7 +378,10 @@ class FastSequentialEngine(GraphTrainEngine):
                     if not first:
                         raise RuntimeError("C_in=1 convolution must be the first layer")
                 elif self._tc_conv(st, B):
-                    acc = self._splitk_acc(("wgrad", li), O, 9 * Cin)
+                    if "wgrad_scratch" not in self._acc32:       # per-CTA fp32 partial tiles (L2 resident)
+                        self._acc32["wgrad_scratch"] = torch.empty(
+                            int(lib.tfy_conv3x3_c32_wgrad_scratch_elems()), dtype=torch.float32, device=dz.device)
+                    acc = self._acc32["wgrad_scratch"]
                     self._chk(lib.tfy_conv3x3_c32_wgrad(xin.data_ptr(), dz.data_ptr(), acc.data_ptr(),
                                                         w.grad.data_ptr(), self._conv_sync.data_ptr(), B, H, W, s),
                               "conv3x3_c32_wgrad")

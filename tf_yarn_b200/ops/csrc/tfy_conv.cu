@@ -2,9 +2,8 @@
 // the second convolution of the MNIST-CNN, forward (fused with bias + ReLU + 2x2 max-pool + dropout),
 // data gradient (fused with the ReLU gate of the previous layer) and weight gradient.
 //
-// Shared-memory operand format (all three kernels).  A CTA works on an 8 x 8 pixel patch of an image
-// PAIR.  TMA (5-D tensor map over the NHWC tensor, channel dimension split into groups of 8) stores a
-// patch as
+// Shared-memory operand format (all three kernels).  A work item is an 8 x 8 pixel patch of an image
+// PAIR, stored as
 //        [channel group][h][image n][w][8 channels = 16 B]
 // i.e. the un-swizzled ("interleave") UMMA canonical layout: a core matrix is 8 consecutive w (8 x 16 B
 // = 128 contiguous bytes), the next core matrix along the pixel dimension is the next (h, n) row, and
@@ -17,11 +16,18 @@
 //   fprop : D[pix, o]  = sum_{t,c} a[pix + t, c] W[o, t, c]     M=128 N=64 K=9x32   (A: K-major, B: K-major)
 //   dgrad : D[pix, c]  = sum_{t,o} dz[pix - t, o] W[o, t, c]    M=128 N=32 K=9x64   (A: K-major, B: MN-major)
 //   wgrad : D[o, (t,c)] = sum_pix dz[pix, o] a[pix + t, c]      M=64  N=32 K=128/patch, 9 accumulators
-//                                                               (A: MN-major, B: MN-major), persistent CTAs
-// Weights ([O][3][3][C] bf16) are loaded by ONE TMA as [tap][c group][o][8 c]: K-major for fprop and,
-// read with the MN-major flag, the transposed operand dgrad needs -- no transpose kernel.
-#include <cuda.h>
-
+//                                                               (A: MN-major, B: MN-major)
+// Weights ([O][3][3][C] bf16) sit in shared memory as [tap][c group][o][8 c]: K-major for fprop and, read
+// with the MN-major flag, the transposed operand dgrad needs -- no transpose kernel.
+//
+// All three are persistent (one CTA per SM walking the patch list) and warp-specialised:
+//   producer warps  : cp.async (16 B, L2 -> smem) gathers into a 3-4 stage ring.  The first version of
+//                     these kernels used 5-D TMA boxes with a 16-byte inner dimension for the same layout;
+//                     ncu showed one L2 request per 16-byte row at ~3 cycles/row/SM (5 B/cycle): 25-33 us
+//                     per kernel (profiles/conv_check_tma_v1_r1h.json).  LSU gathers move 512 B per warp
+//                     instruction instead; TMA keeps the jobs it is good at (the GEMM's 128-byte rows).
+//   MMA warp        : one elected thread issues tcgen05.mma (kind::f16) into a double-buffered TMEM tile
+//   epilogue warps  : tcgen05.ld, fused epilogue, overlapped with the next patch's MMAs
 #include "tfy_common.cuh"
 
 namespace {
@@ -31,28 +37,31 @@ constexpr int CG_IN = CIN / 8, CG_OUT = COUT / 8;
 constexpr int HALO = 10;                               // 8 + 2
 constexpr int ROW_B = HALO * 16;                       // 160  : one (h, n) row of a halo patch
 constexpr int HROW_B = 2 * ROW_B;                      // 320  : one h step (2 images)
-constexpr int HALO_G_B = HALO * HROW_B;                // 3200 : one channel group of a halo patch
-constexpr int PATCH_G_B = 8 * 2 * 8 * 16;              // 2048 : one channel group of an 8x8x2 patch
-constexpr int W_TAP_B = CG_IN * COUT * 16;             // 4096
-constexpr int W_BYTES = TAPS * W_TAP_B;                // 36864
-constexpr int CONV_THREADS = 192;
+constexpr int HALO_G_B = HALO * HROW_B + 16;           // 3216 : channel-group stride of a halo patch (+16: banks)
+constexpr int PATCH_G_B = 8 * 2 * 8 * 16 + 16;         // 2064 : channel-group stride of an 8x8x2 patch
+constexpr int W_G_B = COUT * 16 + 16;                  // 1040 : channel-group stride inside a weight tap
+constexpr int W_TAP_B = CG_IN * W_G_B;                 // 4160
+constexpr int W_BYTES = TAPS * W_TAP_B;                // 37440
+constexpr int PRODUCERS = 128;                         // 4 producer warps
 
-constexpr int FPROP_A_B = CG_IN * HALO_G_B;            // 12800
-constexpr int DGRAD_A_B = CG_OUT * HALO_G_B;           // 25600
-constexpr size_t FPROP_SMEM = FPROP_A_B + W_BYTES + 128 + 128;
-constexpr size_t DGRAD_SMEM = DGRAD_A_B + W_BYTES + 128 + 128;
-constexpr int WG_STAGES = 4;
-constexpr int WG_DZ_B = CG_OUT * PATCH_G_B;            // 16384
-constexpr int WG_STAGE_B = WG_DZ_B + FPROP_A_B;        // 29184
-constexpr size_t WGRAD_SMEM = (size_t)WG_STAGES * WG_STAGE_B + 128 + 256;
+constexpr int FP_STAGES = 3, FP_A_B = CG_IN * HALO_G_B;         // 12864
+constexpr int FP_EPI_WARPS = 16, FP_THREADS = (FP_EPI_WARPS + 1) * 32 + PRODUCERS;  // 672
+constexpr size_t FP_SMEM = (size_t)FP_STAGES * FP_A_B + W_BYTES + 256;
+constexpr int DG_STAGES = 3, DG_A_B = CG_OUT * HALO_G_B;        // 25728
+constexpr int DG_EPI_WARPS = 4, DG_THREADS = (DG_EPI_WARPS + 1) * 32 + PRODUCERS;   // 288
+constexpr size_t DG_SMEM = (size_t)DG_STAGES * DG_A_B + W_BYTES + 256;
+constexpr int WG_STAGES = 4, WG_DZ_B = CG_OUT * PATCH_G_B;      // 16512
+constexpr int WG_STAGE_B = WG_DZ_B + FP_A_B;                    // 29376
+constexpr int WG_THREADS = 288;
+constexpr size_t WG_SMEM = (size_t)WG_STAGES * WG_STAGE_B + 256;
+constexpr int WG_OUT = COUT * TAPS * CIN;                       // 18432
 
 __device__ __forceinline__ uint32_t c_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void c_mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c_smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void c_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(c_smem_u32(bar)), "r"(bytes)
-                 : "memory");
+__device__ __forceinline__ void c_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void c_mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -65,22 +74,17 @@ __device__ __forceinline__ void c_mbar_wait(uint64_t* bar, uint32_t parity) {
         "CDONE:\n\t"
         "}" ::"r"(c_smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void c_tma_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                         int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-        "[%2];" ::"r"(c_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c_smem_u32(bar)), "r"(c0), "r"(c1),
-        "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
+// 16-byte asynchronous copy L2 -> shared (L1 bypass); !valid writes 16 zero bytes without touching memory
+__device__ __forceinline__ void c_cp16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void c_tma_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                         int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-        "[%2];" ::"r"(c_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c_smem_u32(bar)), "r"(c0), "r"(c1),
-        "r"(c2), "r"(c3)
-        : "memory");
-}
+__device__ __forceinline__ void c_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void c_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// generic-proxy writes (cp.async) -> async-proxy reads (tcgen05.mma operand fetch)
+__device__ __forceinline__ void c_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Un-swizzled UMMA shared-memory descriptor.  K-major operand: lbo = byte distance between the two
 // 8-element halves of the K=16 slice, sbo = distance between consecutive groups of 8 rows.  MN-major
 // operand: lbo = distance between consecutive groups of 8 along K, sbo = between groups of 8 along M/N.
@@ -117,8 +121,8 @@ __device__ __forceinline__ void c_tmem_ld16(uint32_t taddr, uint32_t* r) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void c_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 template <int COLS>
 __device__ __forceinline__ void c_tmem_alloc(uint32_t* slot) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(c_smem_u32(slot)),
@@ -132,20 +136,96 @@ __device__ __forceinline__ void c_tmem_free(uint32_t base) {
 }
 __device__ __forceinline__ void c_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void c_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One lane of a CONVERGED warp.  Unlike `lane == 0`, the compiler knows the guarded region runs on exactly
+// one thread and keeps descriptor arithmetic + tcgen05.mma operands in uniform registers; with `lane == 0`
+// every UTCHMMA was wrapped in an ELECT / R2UR / BRA.U.ANY loop (~48 cycles per MMA, measured with
+// tests/gpu/umma_probe.cu).
+__device__ __forceinline__ bool c_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ uint32_t c_hash32(uint32_t x) {
     x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
     return x;
 }
-// must stay identical to tfy_uniform() of tfy_nn.cu (the backward kernels only see the code byte)
-__device__ __forceinline__ float c_uniform(uint32_t seed, uint32_t step, uint64_t idx) {
-    uint32_t h = c_hash32(seed ^ c_hash32(step * 0x9E3779B9U + 0x85ebca6bU) ^
-                          c_hash32((uint32_t)idx * 0xC2B2AE35U + (uint32_t)(idx >> 32) + 0x27d4eb2fU));
-    return (float)(h >> 8) * (1.0f / 16777216.0f);
-}
+// Optional per-CTA event timeline (tests/gpu/conv_check.py --timeline): 16 slots of SM-clock deltas per CTA.
+__device__ long long* c_timeline = nullptr;
+#define C_MARK(k)                                                                  \
+    do {                                                                           \
+        if (c_tl) c_tl[(size_t)blockIdx.x * 16 + (k)] = clock64() - c_t0;          \
+    } while (0)
+#define C_TIMELINE_BEGIN()                 \
+    long long* const c_tl = c_timeline;    \
+    const long long c_t0 = clock64();      \
+    if (c_tl && threadIdx.x == 0) {        \
+        unsigned long long ns;             \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns)); \
+        c_tl[(size_t)blockIdx.x * 16] = (long long)ns;          \
+    }
 
 __device__ __forceinline__ uint8_t* c_align128(uint8_t* p) {
     return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
+}
+
+// ---- producers ------------------------------------------------------------------------------------
+// Gather plan of one producer thread for a [CG][PH h][2 n][PW w][16 B] patch of an NHWC tensor with CG*8
+// channels.  The (source offset, destination offset) pairs depend only on the thread, so they are computed
+// once; per patch a slot costs an add, a predicate and the cp.async (the first version recomputed the
+// h/n/w split with integer divisions per 16-byte chunk and the producers were the critical path of dgrad).
+// Consecutive lanes take consecutive channel groups of a pixel: coalesced 16-byte reads, and the +16 byte
+// group stride spreads the writes over the banks.
+template <int CG, int PH, int PW, int GSTRIDE, bool BOUNDS>
+struct CGather {
+    static constexpr int PIX = PH * 2 * PW;
+    static constexpr int PER_IT = PRODUCERS / CG;
+    static constexpr int NIT = (PIX + PER_IT - 1) / PER_IT;
+    int src[NIT];          // element offset from pixel (b0, y0, x0)
+    uint32_t dst[NIT];     // byte offset inside the stage; 0xffffffff = no slot
+    uint32_t hw[NIT];      // h | w << 8 (bounds checks only)
+
+    __device__ __forceinline__ void init(int ptid, int H, int W) {
+        const int g = ptid % CG;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int p = ptid / CG + it * PER_IT;
+            const bool valid = p < PIX;
+            const int pp = valid ? p : 0;
+            const int h = pp / (2 * PW), rem = pp - h * (2 * PW), n = rem / PW, w = rem - n * PW;
+            src[it] = ((n * H + h) * W + w) * (CG * 8) + g * 8;
+            dst[it] = valid ? (uint32_t)(g * GSTRIDE + (h * 2 + n) * (PW * 16) + w * 16) : 0xffffffffu;
+            hw[it] = (uint32_t)h | ((uint32_t)w << 8);
+        }
+    }
+    // tensor: base pointer; (b0, y0, x0): patch origin, possibly outside the image when BOUNDS
+    __device__ __forceinline__ void issue(uint32_t stage, const __nv_bfloat16* __restrict__ tensor, int H, int W, int b0,
+                                          int y0, int x0) const {
+        const long long origin = (((long long)b0 * H + y0) * W + x0) * (CG * 8);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            if (dst[it] != 0xffffffffu) {
+                bool ok = true;
+                if (BOUNDS) {
+                    const int y = y0 + (int)(hw[it] & 0xffu), x = x0 + (int)(hw[it] >> 8);
+                    ok = (unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W;
+                }
+                c_cp16(stage + dst[it], tensor + (ok ? origin + src[it] : 0), ok);
+            }
+        }
+    }
+};
+using CHaloIn = CGather<CG_IN, HALO, HALO, HALO_G_B, false>;       // activations, always inside the image
+using CHaloOut = CGather<CG_OUT, HALO, HALO, HALO_G_B, true>;      // dz with zero padding (dgrad)
+using CPatchOut = CGather<CG_OUT, 8, 8, PATCH_G_B, false>;         // dz patch (wgrad)
+
+// weights [O][9][C] -> [tap][c group][o][8 c]
+__device__ __forceinline__ void c_load_weights(uint32_t dst, const __nv_bfloat16* __restrict__ w, int ptid) {
+#pragma unroll 1
+    for (int q = ptid; q < COUT * TAPS * CG_IN; q += PRODUCERS) {
+        const int o = q / (TAPS * CG_IN), r = q - o * (TAPS * CG_IN), t = r / CG_IN, g = r - t * CG_IN;
+        c_cp16(dst + t * W_TAP_B + g * W_G_B + o * 16, w + (size_t)q * 8, true);
+    }
 }
 
 }  // namespace
@@ -153,217 +233,322 @@ __device__ __forceinline__ uint8_t* c_align128(uint8_t* p) {
 // ------------------------------------------------------------------------------------------------
 // forward: pooled = dropout(maxpool2x2(relu(conv(a, W) + bias))), code byte per pooled element
 // (bits 0-1 = argmax position dy*2+dx inside the 2x2 window, bit 2 = gradient flows).
-// grid = (OW/8, OH/8, B/2)
+// warps 0..15 epilogue (TMEM quadrant = warp & 3, 16-column slice = warp >> 2), warp 16 MMA, warps 17..20 producers
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CONV_THREADS, 4)
-tfy_conv3x3_fprop_pool_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+__global__ void __launch_bounds__(FP_THREADS, 1)
+tfy_conv3x3_fprop_pool_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ wgt,
                               const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ pooled,
-                              uint8_t* __restrict__ code, int OH, int OW, float drop_rate, uint32_t seed,
-                              const TfyOptHyper* __restrict__ hp) {
+                              uint8_t* __restrict__ code, int H, int W, int tiles_x, int tiles_y, int n_patches,
+                              float drop_rate, uint32_t seed, const TfyOptHyper* __restrict__ hp) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* a_tile = c_align128(smem_raw);                   // [4][10][2][10][16 B]
-    uint8_t* w_tile = a_tile + FPROP_A_B;                     // [9][4][64][16 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(w_tile + W_BYTES);   // 0: operands landed, 1: accumulator ready
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    C_TIMELINE_BEGIN();
+    uint8_t* stages = c_align128(smem_raw);
+    uint8_t* w_tile = stages + (size_t)FP_STAGES * FP_A_B;
+    uint64_t* full = reinterpret_cast<uint64_t*>(w_tile + W_BYTES);
+    uint64_t* empty = full + FP_STAGES;
+    uint64_t* tfull = empty + FP_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ow0 = blockIdx.x * 8, oh0 = blockIdx.y * 8, b0 = blockIdx.z * 2;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-        c_mbar_init(&bars[0], 1);
-        c_mbar_init(&bars[1], 1);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FP_STAGES; ++s) { c_mbar_init(&full[s], PRODUCERS); c_mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { c_mbar_init(&tfull[b], 1); c_mbar_init(&tempty[b], FP_EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) c_tmem_alloc<64>(tmem_slot);
+    if (warp == FP_EPI_WARPS) c_tmem_alloc<128>(tmem_slot);
     c_fence_before();
     __syncthreads();
     c_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) C_MARK(1);
+    const int my_patches = ((int)blockIdx.x < n_patches) ? (n_patches - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int tiles = tiles_x * tiles_y;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            c_mbar_expect_tx(&bars[0], FPROP_A_B + W_BYTES);
-            c_tma_5d(&map_a, &bars[0], a_tile, 0, ow0, b0, oh0, 0);
-            c_tma_4d(&map_w, &bars[0], w_tile, 0, 0, 0, 0);
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = c_idesc(128, COUT, 0, 0);
-            const uint32_t a0 = c_smem_u32(a_tile), w0 = c_smem_u32(w_tile);
-            c_mbar_wait(&bars[0], 0);
-            c_fence_after();
-#pragma unroll 1
-            for (int t = 0; t < TAPS; ++t) {
-                const int kh = t / 3, kw = t % 3;
-#pragma unroll
-                for (int ks = 0; ks < CIN / 16; ++ks) {
-                    // A: rows = pixels (8 w per core matrix, (h,n) groups ROW_B apart), K halves = channel groups
-                    const uint64_t adesc = c_desc(a0 + kh * HROW_B + kw * 16 + ks * 2 * HALO_G_B, HALO_G_B, ROW_B);
-                    // B: rows = output channels (16 B apart, groups of 8 = 128 B), K halves = channel groups
-                    const uint64_t bdesc = c_desc(w0 + t * W_TAP_B + ks * 2 * (COUT * 16), COUT * 16, 128);
-                    c_umma(tmem_base, adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u);
-                }
+    if (warp > FP_EPI_WARPS) {
+        // ---------------- producers
+        const int ptid = threadIdx.x - (FP_EPI_WARPS + 1) * 32;
+        constexpr int LAG = FP_STAGES - 1;
+        CHaloIn plan;
+        plan.init(ptid, H, W);
+        for (int i = 0; i < my_patches; ++i) {
+            const int s = i % FP_STAGES;
+            if (i >= FP_STAGES) c_mbar_wait(&empty[s], ((i / FP_STAGES) - 1) & 1);
+            const int p = (int)blockIdx.x + i * (int)gridDim.x;
+            const int bz = p / tiles, r = p - bz * tiles, ty = r / tiles_x, tx = r - ty * tiles_x;
+            if (i == 0) c_load_weights(c_smem_u32(w_tile), wgt, ptid);
+            plan.issue(c_smem_u32(stages + (size_t)s * FP_A_B), a, H, W, bz * 2, ty * 8, tx * 8);
+            c_cp_commit();
+            if (i == 0 && ptid == 0) C_MARK(2);
+            if (i >= LAG) {
+                c_cp_wait<LAG>();
+                c_fence_async_smem();
+                if (i == LAG && ptid == 0) C_MARK(3);
+                c_mbar_arrive(&full[(i - LAG) % FP_STAGES]);
             }
-            c_commit(&bars[1]);
+        }
+        c_cp_wait<0>();
+        c_fence_async_smem();
+        if (ptid == 0) C_MARK(12);
+        for (int i = (my_patches > LAG ? my_patches - LAG : 0); i < my_patches; ++i) c_mbar_arrive(&full[i % FP_STAGES]);
+    } else if (warp == FP_EPI_WARPS) {
+        // ---------------- MMA issuer
+        if (c_elect_one()) {
+            const uint32_t idesc = c_idesc(128, COUT, 0, 0);
+            const uint32_t w0 = c_smem_u32(w_tile);
+            for (int i = 0; i < my_patches; ++i) {
+                const int s = i % FP_STAGES, b = i & 1;
+                c_mbar_wait(&full[s], (i / FP_STAGES) & 1);
+                if (i == 0) C_MARK(4);
+                c_fence_async_smem();
+                if (i >= 2) c_mbar_wait(&tempty[b], ((i >> 1) - 1) & 1);
+                c_fence_after();
+                const uint32_t a0 = c_smem_u32(stages + (size_t)s * FP_A_B);
+#pragma unroll 1
+                for (int t = 0; t < TAPS; ++t) {
+                    const int kh = t / 3, kw = t - kh * 3;
+#pragma unroll
+                    for (int ks = 0; ks < CIN / 16; ++ks) {
+                        // A: rows = pixels (8 w per core matrix, (h,n) groups ROW_B apart), K halves = channel groups
+                        const uint64_t adesc = c_desc(a0 + kh * HROW_B + kw * 16 + ks * 2 * HALO_G_B, HALO_G_B, ROW_B);
+                        // B: rows = output channels (16 B apart, groups of 8 = 128 B), K halves = channel groups
+                        const uint64_t bdesc = c_desc(w0 + t * W_TAP_B + ks * 2 * W_G_B, W_G_B, 128);
+                        c_umma(tmem_base + (uint32_t)(b * COUT), adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                c_commit(&empty[s]);
+                c_commit(&tfull[b]);
+                if (i == 0) C_MARK(5);
+                if (i == my_patches - 1) C_MARK(11);
+            }
         }
     } else {
-        // epilogue warps 2..5 own TMEM lane quadrants 2,3,0,1.  Accumulator row r = (h, n, w) = (r/16, (r/8)&1, r%8)
-        const int quad = warp & 3;
-        c_mbar_wait(&bars[1], 0);
-        c_fence_after();
+        // ---------------- epilogue: accumulator row r = (h, n, w) = (r/16, (r/8)&1, r%8) lives in TMEM lane r
+        const int quad = warp & 3, cq = warp >> 2;
         const int r = quad * 32 + lane;
         const int h = r >> 4, n = (r >> 3) & 1, w = r & 7;
-        const int PH = OH / 2, PW = OW / 2;
+        const int dx = lane & 1, dy = (lane >> 4) & 1;            // position inside the 2x2 pooling window
+        const uint32_t tag = (uint32_t)(dy * 2 + dx);
+        const int OH = H - 2, OW = W - 2, PH = OH / 2, PW = OW / 2;
         const uint32_t step = hp ? (uint32_t)hp->step : 0u;
-        const float keep_scale = drop_rate > 0.f ? 1.f / (1.f - drop_rate) : 1.f;
-        const bool writer = ((lane & 16) == 0) && ((lane & 1) == 0);          // h even, w even
-        const size_t prow = (((size_t)(b0 + n) * PH + (oh0 + h) / 2) * PW + (ow0 + w) / 2) * COUT;
-#pragma unroll 1
-        for (int c = 0; c < COUT; c += 16) {
+        // dropout decisions come 4 to a hash (one byte each): the rate is quantised to 1/256
+        const uint32_t thr = drop_rate > 0.f ? (uint32_t)(drop_rate * 256.f + 0.5f) : 0u;
+        const float keep_scale = 256.f / (256.f - (float)thr);
+        const uint32_t salt = seed ^ c_hash32(step * 0x9E3779B9U + 0x85ebca6bU);
+        // after the two exchanges below lane (dy, dx) owns columns [8 dx + 4 dy, +4) of the warp's 16
+        const int col = cq * 16 + dx * 8 + dy * 4;
+        const uint2 braw = *reinterpret_cast<const uint2*>(bias + col);
+        const float bv[4] = {tfy_bf16lo(braw.x), tfy_bf16hi(braw.x), tfy_bf16lo(braw.y), tfy_bf16hi(braw.y)};
+        for (int i = 0; i < my_patches; ++i) {
+            const int b = i & 1;
+            const int p = (int)blockIdx.x + i * (int)gridDim.x;
+            const int bz = p / tiles, rr = p - bz * tiles, ty = rr / tiles_x, tx = rr - ty * tiles_x;
+            const size_t prow = (((size_t)(bz * 2 + n) * PH + (ty * 8 + h) / 2) * PW + (tx * 8 + w) / 2) * COUT;
+            c_mbar_wait(&tfull[b], (i >> 1) & 1);
+            if (threadIdx.x == 0) { if (i == 0) C_MARK(6); if (i == my_patches - 1) C_MARK(8); }
+            c_fence_after();
             uint32_t acc[16];
-            c_tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, acc);
-            float outv[16];
-            uint32_t codes[4] = {0, 0, 0, 0};
+            c_tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * COUT + cq * 16), acc);
+            c_tmem_ld_wait();
+            c_fence_before();
+            c_mbar_arrive(&tempty[b]);                             // the MMA warp may overwrite this buffer now
+            // tag every value with its window position in the 2 low mantissa bits, then reduce-scatter the
+            // max over the window (lane ^ 1: other column, lane ^ 16: other row)
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float v = __uint_as_float(acc[j]);
-                // window of the (even h, even w) lane: itself (0,0), lane^1 (0,1), lane^16 (1,0), lane^17 (1,1)
-                const float v01 = __shfl_xor_sync(0xffffffffu, v, 1);
-                const float v10 = __shfl_xor_sync(0xffffffffu, v, 16);
-                const float v11 = __shfl_xor_sync(0xffffffffu, v, 17);
-                float best = v;
-                int arg = 0;
-                if (v01 > best) { best = v01; arg = 1; }
-                if (v10 > best) { best = v10; arg = 2; }
-                if (v11 > best) { best = v11; arg = 3; }
-                float o = best + __bfloat162float(bias[c + j]);
-                bool on = o > 0.f;
-                o = on ? o : 0.f;
-                if (drop_rate > 0.f) {
-                    const bool keep = c_uniform(seed, step, prow + c + j) >= drop_rate;
-                    o = keep ? o * keep_scale : 0.f;
-                    on = on && keep;
-                }
-                outv[j] = o;
-                codes[j >> 2] |= ((uint32_t)arg | (on ? 4u : 0u)) << (8 * (j & 3));
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float((acc[j] & ~3u) | tag);
+            float m8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float send = dx ? v[j] : v[8 + j];
+                const float keep = dx ? v[8 + j] : v[j];
+                m8[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
             }
-            if (writer) {
-                tfy_st16(pooled + prow + c, TfyPack<__nv_bfloat16>::pack(outv));
-                tfy_st16(pooled + prow + c + 8, TfyPack<__nv_bfloat16>::pack(outv + 8));
-                *reinterpret_cast<uint4*>(code + prow + c) = make_uint4(codes[0], codes[1], codes[2], codes[3]);
+            float m4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float send = dy ? m8[j] : m8[4 + j];
+                const float keep = dy ? m8[4 + j] : m8[j];
+                m4[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
             }
+            const uint32_t rnd =
+                thr ? c_hash32(salt ^ c_hash32((uint32_t)((prow + col) >> 2) * 0xC2B2AE35U + 0x27d4eb2fU)) : 0xffffffffu;
+            float o[4];
+            uint32_t codes = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t pos = __float_as_uint(m4[j]) & 3u;
+                float x = m4[j] + bv[j];
+                const bool on = x > 0.f && ((rnd >> (8 * j)) & 0xffu) >= thr;
+                x = on ? x * keep_scale : 0.f;
+                o[j] = x;
+                codes |= (pos | (on ? 4u : 0u)) << (8 * j);
+            }
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+            uint2 packed;
+            packed.x = *reinterpret_cast<uint32_t*>(&lo);
+            packed.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(pooled + prow + col) = packed;
+            *reinterpret_cast<uint32_t*>(code + prow + col) = codes;
+            if (threadIdx.x == 0) { if (i == 0) C_MARK(7); if (i == my_patches - 1) C_MARK(9); }
         }
     }
     c_fence_before();
     __syncthreads();
-    if (warp == 1) c_tmem_free<64>(tmem_base);
+    if (warp == FP_EPI_WARPS) c_tmem_free<128>(tmem_base);
+    if (threadIdx.x == 0) C_MARK(10);
 }
 
 // ------------------------------------------------------------------------------------------------
 // data gradient: dx[b, y, x, c] = sum_{kh,kw,o} dz[b, y-kh, x-kw, o] W[o, kh, kw, c], optionally gated by
 // the previous layer's ReLU (gate = that layer's output: dx is zeroed where gate <= 0).
-// dz: [B, H-2, W-2, 64]; dx: [B, H, W, 32].  grid = (ceil(W/8), ceil(H/8), B/2); TMA zero-fills the halo.
+// dz: [B, H-2, W-2, 64]; dx: [B, H, W, 32].  warps 0..3 epilogue, warp 4 MMA, warps 5..8 producers
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CONV_THREADS, 3)
-tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_w,
-                         const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ dx, int H, int W) {
+__global__ void __launch_bounds__(DG_THREADS, 1)
+tfy_conv3x3_dgrad_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ wgt,
+                         const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ dx, int H, int W,
+                         int tiles_x, int tiles_y, int n_patches) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* a_tile = c_align128(smem_raw);                   // [8][10][2][10][16 B]
-    uint8_t* w_tile = a_tile + DGRAD_A_B;                     // [9][4][64][16 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(w_tile + W_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    C_TIMELINE_BEGIN();
+    uint8_t* stages = c_align128(smem_raw);
+    uint8_t* w_tile = stages + (size_t)DG_STAGES * DG_A_B;
+    uint64_t* full = reinterpret_cast<uint64_t*>(w_tile + W_BYTES);
+    uint64_t* empty = full + DG_STAGES;
+    uint64_t* tfull = empty + DG_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x0 = blockIdx.x * 8, y0 = blockIdx.y * 8, b0 = blockIdx.z * 2;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_dz)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-        c_mbar_init(&bars[0], 1);
-        c_mbar_init(&bars[1], 1);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < DG_STAGES; ++s) { c_mbar_init(&full[s], PRODUCERS); c_mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { c_mbar_init(&tfull[b], 1); c_mbar_init(&tempty[b], DG_EPI_WARPS * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) c_tmem_alloc<32>(tmem_slot);
+    if (warp == DG_EPI_WARPS) c_tmem_alloc<64>(tmem_slot);
     c_fence_before();
     __syncthreads();
     c_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) C_MARK(1);
+    const int my_patches = ((int)blockIdx.x < n_patches) ? (n_patches - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int tiles = tiles_x * tiles_y;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            c_mbar_expect_tx(&bars[0], DGRAD_A_B + W_BYTES);
-            c_tma_5d(&map_dz, &bars[0], a_tile, 0, x0 - 2, b0, y0 - 2, 0);     // out-of-range pixels read as zero
-            c_tma_4d(&map_w, &bars[0], w_tile, 0, 0, 0, 0);
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = c_idesc(128, CIN, 0, 1);                    // B is MN-major: N = c contiguous
-            const uint32_t a0 = c_smem_u32(a_tile), w0 = c_smem_u32(w_tile);
-            c_mbar_wait(&bars[0], 0);
-            c_fence_after();
-#pragma unroll 1
-            for (int t = 0; t < TAPS; ++t) {
-                const int kh = t / 3, kw = t % 3;
-#pragma unroll
-                for (int ks = 0; ks < COUT / 16; ++ks) {
-                    // halo origin is (y0-2, x0-2): dz[y-kh, x-kw] sits (2-kh, 2-kw) into the patch
-                    const uint64_t adesc =
-                        c_desc(a0 + (2 - kh) * HROW_B + (2 - kw) * 16 + ks * 2 * HALO_G_B, HALO_G_B, ROW_B);
-                    // W tap as [c group][o][8 c]: K = o (16 B apart, groups of 8 o = 128 B), N groups = c groups
-                    const uint64_t bdesc = c_desc(w0 + t * W_TAP_B + ks * 16 * 16, 128, COUT * 16);
-                    c_umma(tmem_base, adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u);
-                }
+    if (warp > DG_EPI_WARPS) {
+        const int ptid = threadIdx.x - (DG_EPI_WARPS + 1) * 32;
+        constexpr int LAG = DG_STAGES - 1;
+        CHaloOut plan;
+        plan.init(ptid, H - 2, W - 2);
+        for (int i = 0; i < my_patches; ++i) {
+            const int s = i % DG_STAGES;
+            if (i >= DG_STAGES) c_mbar_wait(&empty[s], ((i / DG_STAGES) - 1) & 1);
+            const int p = (int)blockIdx.x + i * (int)gridDim.x;
+            const int bz = p / tiles, r = p - bz * tiles, ty = r / tiles_x, tx = r - ty * tiles_x;
+            if (i == 0) c_load_weights(c_smem_u32(w_tile), wgt, ptid);
+            // halo origin (y0-2, x0-2) of the dz image (H-2 x W-2): pixels outside it read as zero
+            plan.issue(c_smem_u32(stages + (size_t)s * DG_A_B), dz, H - 2, W - 2, bz * 2, ty * 8 - 2, tx * 8 - 2);
+            c_cp_commit();
+            if (i == 0 && ptid == 0) C_MARK(2);
+            if (i >= LAG) {
+                c_cp_wait<LAG>();
+                c_fence_async_smem();
+                if (i == LAG && ptid == 0) C_MARK(3);
+                c_mbar_arrive(&full[(i - LAG) % DG_STAGES]);
             }
-            c_commit(&bars[1]);
+        }
+        c_cp_wait<0>();
+        c_fence_async_smem();
+        if (ptid == 0) C_MARK(12);
+        for (int i = (my_patches > LAG ? my_patches - LAG : 0); i < my_patches; ++i) c_mbar_arrive(&full[i % DG_STAGES]);
+    } else if (warp == DG_EPI_WARPS) {
+        if (c_elect_one()) {
+            const uint32_t idesc = c_idesc(128, CIN, 0, 1);                    // B is MN-major: N = c contiguous
+            const uint32_t w0 = c_smem_u32(w_tile);
+            for (int i = 0; i < my_patches; ++i) {
+                const int s = i % DG_STAGES, b = i & 1;
+                c_mbar_wait(&full[s], (i / DG_STAGES) & 1);
+                if (i == 0) C_MARK(4);
+                c_fence_async_smem();
+                if (i >= 2) c_mbar_wait(&tempty[b], ((i >> 1) - 1) & 1);
+                c_fence_after();
+                const uint32_t a0 = c_smem_u32(stages + (size_t)s * DG_A_B);
+#pragma unroll 1
+                for (int t = 0; t < TAPS; ++t) {
+                    const int kh = t / 3, kw = t - kh * 3;
+#pragma unroll
+                    for (int ks = 0; ks < COUT / 16; ++ks) {
+                        // dz[y-kh, x-kw] sits (2-kh, 2-kw) into the halo patch
+                        const uint64_t adesc =
+                            c_desc(a0 + (2 - kh) * HROW_B + (2 - kw) * 16 + ks * 2 * HALO_G_B, HALO_G_B, ROW_B);
+                        // W tap as [c group][o][8 c]: K = o (16 B apart, groups of 8 o = 128 B), N groups = c groups
+                        const uint64_t bdesc = c_desc(w0 + t * W_TAP_B + ks * 16 * 16, 128, W_G_B);
+                        c_umma(tmem_base + (uint32_t)(b * CIN), adesc, bdesc, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                c_commit(&empty[s]);
+                c_commit(&tfull[b]);
+                if (i == 0) C_MARK(5);
+                if (i == my_patches - 1) C_MARK(11);
+            }
         }
     } else {
         const int quad = warp & 3;
-        c_mbar_wait(&bars[1], 0);
-        c_fence_after();
         const int r = quad * 32 + lane;
         const int h = r >> 4, n = (r >> 3) & 1, w = r & 7;
-        const int y = y0 + h, x = x0 + w;
-        const bool valid = y < H && x < W;
-        const size_t off = (((size_t)(b0 + n) * H + y) * W + x) * CIN;
+        for (int i = 0; i < my_patches; ++i) {
+            const int b = i & 1;
+            const int p = (int)blockIdx.x + i * (int)gridDim.x;
+            const int bz = p / tiles, rr = p - bz * tiles, ty = rr / tiles_x, tx = rr - ty * tiles_x;
+            c_mbar_wait(&tfull[b], (i >> 1) & 1);
+            if (threadIdx.x == 0) { if (i == 0) C_MARK(6); if (i == my_patches - 1) C_MARK(8); }
+            c_fence_after();
+            uint32_t acc[2][16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * CIN);
+            c_tmem_ld16(taddr, acc[0]);
+            c_tmem_ld16(taddr + 16, acc[1]);
+            c_tmem_ld_wait();
+            c_fence_before();
+            c_mbar_arrive(&tempty[b]);
+            const int y = ty * 8 + h, x = tx * 8 + w;
+            if (y < H && x < W) {
+                const size_t off = (((size_t)(bz * 2 + n) * H + y) * W + x) * CIN;
 #pragma unroll
-        for (int c = 0; c < CIN; c += 16) {
-            uint32_t acc[16];
-            c_tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, acc);
-            if (valid) {
-                float v[16];
+                for (int ch = 0; ch < 2; ++ch) {
+                    float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-                if (gate) {
-                    float g[16];
-                    TfyPack<__nv_bfloat16>::unpack(tfy_ld16(gate + off + c), g);
-                    TfyPack<__nv_bfloat16>::unpack(tfy_ld16(gate + off + c + 8), g + 8);
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[ch][j]);
+                    if (gate) {
+                        float g[16];
+                        TfyPack<__nv_bfloat16>::unpack(tfy_ld16(gate + off + ch * 16), g);
+                        TfyPack<__nv_bfloat16>::unpack(tfy_ld16(gate + off + ch * 16 + 8), g + 8);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = g[j] > 0.f ? v[j] : 0.f;
+                        for (int j = 0; j < 16; ++j) v[j] = g[j] > 0.f ? v[j] : 0.f;
+                    }
+                    tfy_st16(dx + off + ch * 16, TfyPack<__nv_bfloat16>::pack(v));
+                    tfy_st16(dx + off + ch * 16 + 8, TfyPack<__nv_bfloat16>::pack(v + 8));
                 }
-                tfy_st16(dx + off + c, TfyPack<__nv_bfloat16>::pack(v));
-                tfy_st16(dx + off + c + 8, TfyPack<__nv_bfloat16>::pack(v + 8));
             }
         }
     }
     c_fence_before();
     __syncthreads();
-    if (warp == 1) c_tmem_free<32>(tmem_base);
+    if (warp == DG_EPI_WARPS) c_tmem_free<64>(tmem_base);
+    if (threadIdx.x == 0) C_MARK(10);
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight gradient: dW[o, t, c] = sum_{b,y,x} dz[b, y, x, o] a[b, y+kh, x+kw, c].  Persistent CTAs walk the
-// 8x8x2 pixel patches (the GEMM K dimension) through a TMA ring, accumulating nine 64x32 tiles in TMEM
-// (one per tap: 288 of the 512 columns); partial sums meet in a zeroed fp32 buffer (red.global.add.v4.f32)
-// and, after a grid-wide arrive/release, every CTA converts and re-zeroes its slice of it.
-// acc32: [64*288] floats, zero on entry (left zero on exit); sync: two uint32, zero-initialised once.
+// weight gradient: dW[o, t, c] = sum_{b,y,x} dz[b, y, x, o] a[b, y+kh, x+kw, c].  The pixel patches are the
+// GEMM K dimension: every CTA accumulates nine 64x32 tiles in TMEM (one per tap: 288 of the 512 columns)
+// over its share of the patches, stores the partial to `partials[blockIdx.x]` (fp32, L2 resident), and after
+// a grid-wide arrive/release reduces a slice of the 18432 outputs over all partials in a fixed order
+// (deterministic, no atomics) and writes bf16 dW.
+// warps 0..3 epilogue, warp 4 MMA, warps 5..8 producers.  sync: two uint32, zero-initialised once.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CONV_THREADS, 1)
-tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_a,
-                         float* __restrict__ acc32, __nv_bfloat16* __restrict__ dw, uint32_t* __restrict__ sync,
-                         int tiles_x, int tiles_y, int n_patches) {
+__global__ void __launch_bounds__(WG_THREADS, 1)
+tfy_conv3x3_wgrad_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ dz,
+                         float* __restrict__ partials, __nv_bfloat16* __restrict__ dw, uint32_t* __restrict__ sync,
+                         int H, int W, int tiles_x, int tiles_y, int n_patches) {
     extern __shared__ uint8_t smem_raw[];
+    C_TIMELINE_BEGIN();
     uint8_t* stages = c_align128(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)WG_STAGES * WG_STAGE_B);
     uint64_t* empty = full + WG_STAGES;
@@ -372,45 +557,61 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t gen0 = threadIdx.x == 0 ? *reinterpret_cast<volatile uint32_t*>(sync + 1) : 0u;
-
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_dz)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
-        for (int s = 0; s < WG_STAGES; ++s) { c_mbar_init(&full[s], 1); c_mbar_init(&empty[s], 1); }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { c_mbar_init(&full[s], PRODUCERS); c_mbar_init(&empty[s], 1); }
         c_mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) c_tmem_alloc<512>(tmem_slot);
+    if (warp == 4) c_tmem_alloc<512>(tmem_slot);
     c_fence_before();
     __syncthreads();
     c_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) C_MARK(1);
     const int my_patches = ((int)blockIdx.x < n_patches) ? (n_patches - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int tiles = tiles_x * tiles_y;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int i = 0; i < my_patches; ++i) {
-                const int s = i % WG_STAGES;
-                if (i >= WG_STAGES) c_mbar_wait(&empty[s], ((i / WG_STAGES) - 1) & 1);
-                const int p = (int)blockIdx.x + i * (int)gridDim.x;
-                const int tx = p % tiles_x, ty = (p / tiles_x) % tiles_y, bz = p / (tiles_x * tiles_y);
-                uint8_t* st = stages + (size_t)s * WG_STAGE_B;
-                c_mbar_expect_tx(&full[s], WG_STAGE_B);
-                c_tma_5d(&map_dz, &full[s], st, 0, tx * 8, bz * 2, ty * 8, 0);            // [8 og][8 h][2 n][8 w][8 o]
-                c_tma_5d(&map_a, &full[s], st + WG_DZ_B, 0, tx * 8, bz * 2, ty * 8, 0);   // [4 cg][10 h][2 n][10 w][8 c]
+    if (warp > 4) {
+        const int ptid = threadIdx.x - 5 * 32;
+        constexpr int LAG = WG_STAGES - 1;
+        CPatchOut plan_dz;
+        CHaloIn plan_a;
+        plan_dz.init(ptid, H - 2, W - 2);
+        plan_a.init(ptid, H, W);
+        for (int i = 0; i < my_patches; ++i) {
+            const int s = i % WG_STAGES;
+            if (i >= WG_STAGES) c_mbar_wait(&empty[s], ((i / WG_STAGES) - 1) & 1);
+            const int p = (int)blockIdx.x + i * (int)gridDim.x;
+            const int bz = p / tiles, r = p - bz * tiles, ty = r / tiles_x, tx = r - ty * tiles_x;
+            const uint32_t st = c_smem_u32(stages + (size_t)s * WG_STAGE_B);
+            plan_dz.issue(st, dz, H - 2, W - 2, bz * 2, ty * 8, tx * 8);
+            plan_a.issue(st + WG_DZ_B, a, H, W, bz * 2, ty * 8, tx * 8);
+            c_cp_commit();
+            if (i == 0 && ptid == 0) C_MARK(2);
+            if (i >= LAG) {
+                c_cp_wait<LAG>();
+                c_fence_async_smem();
+                if (i == LAG && ptid == 0) C_MARK(3);
+                c_mbar_arrive(&full[(i - LAG) % WG_STAGES]);
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+        c_cp_wait<0>();
+        c_fence_async_smem();
+        if (ptid == 0) C_MARK(12);
+        for (int i = (my_patches > LAG ? my_patches - LAG : 0); i < my_patches; ++i) c_mbar_arrive(&full[i % WG_STAGES]);
+    } else if (warp == 4) {
+        if (c_elect_one()) {
             const uint32_t idesc = c_idesc(64, CIN, 1, 1);
             for (int i = 0; i < my_patches; ++i) {
                 const int s = i % WG_STAGES;
                 c_mbar_wait(&full[s], (i / WG_STAGES) & 1);
+                if (i == 0) C_MARK(4);
+                c_fence_async_smem();
                 c_fence_after();
                 const uint32_t dz0 = c_smem_u32(stages + (size_t)s * WG_STAGE_B), a0 = dz0 + WG_DZ_B;
 #pragma unroll 1
                 for (int t = 0; t < TAPS; ++t) {
-                    const int kh = t / 3, kw = t % 3;
+                    const int kh = t / 3, kw = t - kh * 3;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {          // 16 pixels (one h row of both images) per MMA
                         // A = dz^T: M = o (8 per 16 B; o groups PATCH_G_B apart), K = pixels (8 w = 128 B per group)
@@ -423,32 +624,38 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
                 c_commit(&empty[s]);                        // smem stage reusable once these MMAs retire
             }
             c_commit(tmem_full);
+            C_MARK(5);
         }
     } else if (my_patches > 0) {
         // M = 64 accumulator: row o lives in TMEM lane (o % 16) + 32 * (o / 16): lanes 0..15 of each quadrant
         const int quad = warp & 3;
         c_mbar_wait(tmem_full, 0);
+        if (threadIdx.x == 0) C_MARK(6);
         c_fence_after();
-        const int o = quad * 16 + lane;
+        float* mine = partials + (size_t)blockIdx.x * WG_OUT + (size_t)(quad * 16 + (lane & 15)) * (TAPS * CIN);
 #pragma unroll 1
-        for (int col = 0; col < TAPS * CIN; col += 16) {
-            uint32_t acc[16];
-            c_tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, acc);
+        for (int col = 0; col < TAPS * CIN; col += 32) {
+            uint32_t acc[2][16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col;
+            c_tmem_ld16(taddr, acc[0]);
+            c_tmem_ld16(taddr + 16, acc[1]);
+            c_tmem_ld_wait();
             if (lane < 16) {
-                float* dst = acc32 + (size_t)o * (TAPS * CIN) + col;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
-                                 "f"(__uint_as_float(acc[j])), "f"(__uint_as_float(acc[j + 1])),
-                                 "f"(__uint_as_float(acc[j + 2])), "f"(__uint_as_float(acc[j + 3]))
-                                 : "memory");
+                for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        __stcg(reinterpret_cast<float4*>(mine + col + ch * 16 + j),
+                               make_float4(__uint_as_float(acc[ch][j]), __uint_as_float(acc[ch][j + 1]),
+                                           __uint_as_float(acc[ch][j + 2]), __uint_as_float(acc[ch][j + 3])));
             }
         }
         __threadfence();
     }
     c_fence_before();
     __syncthreads();
-    if (warp == 1) c_tmem_free<512>(tmem_base);
+    if (warp == 4) c_tmem_free<512>(tmem_base);
+    if (threadIdx.x == 0) C_MARK(7);
 
     // grid-wide arrive / release (all CTAs are co-resident: grid <= #SMs, one CTA per SM)
     if (threadIdx.x == 0) {
@@ -459,88 +666,111 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
             __threadfence();
             atomicAdd(sync + 1, 1u);
         } else {
-            while (*reinterpret_cast<volatile uint32_t*>(sync + 1) == gen0) __nanosleep(32);
+            while (*reinterpret_cast<volatile uint32_t*>(sync + 1) == gen0) __nanosleep(20);
         }
         __threadfence();
     }
     __syncthreads();
-    constexpr int TOTAL4 = COUT * TAPS * CIN / 4;
-    for (int i = (int)blockIdx.x * CONV_THREADS + (int)threadIdx.x; i < TOTAL4; i += (int)gridDim.x * CONV_THREADS) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(acc32) + i);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    if (threadIdx.x == 0) C_MARK(8);
+    // slice of the outputs owned by this CTA (float4 units), summed over the partials in a fixed order
+    constexpr int TOTAL4 = WG_OUT / 4;
+    const int per = (TOTAL4 + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = (int)blockIdx.x * per, hi = min(lo + per, TOTAL4);
+    const int len = max(hi - lo, 0);
+    const int n_part = (int)gridDim.x;                               // every CTA wrote a partial
+    const float4* src = reinterpret_cast<const float4*>(partials) + lo;
+    auto store = [&](int f, const float4& s4) {
+        __nv_bfloat162 l2 = __floats2bfloat162_rn(s4.x, s4.y), h2 = __floats2bfloat162_rn(s4.z, s4.w);
         uint2 packed;
-        packed.x = *reinterpret_cast<uint32_t*>(&lo);
-        packed.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(dw + (size_t)i * 4) = packed;
-        __stcg(reinterpret_cast<float4*>(acc32) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+        packed.x = *reinterpret_cast<uint32_t*>(&l2);
+        packed.y = *reinterpret_cast<uint32_t*>(&h2);
+        *reinterpret_cast<uint2*>(dw + (size_t)(lo + f) * 4) = packed;
+    };
+    if (len > 0 && 2 * len <= WG_THREADS) {
+        // few outputs per CTA (the usual case: 32): `parts` thread groups split the list of partials
+        float4* red = reinterpret_cast<float4*>(stages);             // the ring is idle now
+        const int parts = min(WG_THREADS / len, 16);
+        const int f = (int)threadIdx.x % len, part = (int)threadIdx.x / len;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (part < parts) {
+#pragma unroll 8
+            for (int q = part; q < n_part; q += parts) {
+                const float4 v = __ldcg(src + (size_t)q * TOTAL4 + f);
+                s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+            }
+        }
+        red[threadIdx.x] = s4;
+        __syncthreads();
+        if (part == 0) {
+            for (int q = 1; q < parts; ++q) {
+                const float4 v = red[q * len + f];
+                s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+            }
+            store(f, s4);
+        }
+    } else {
+        for (int f = (int)threadIdx.x; f < len; f += WG_THREADS) {
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int q = 0; q < n_part; ++q) {
+                const float4 v = __ldcg(src + (size_t)q * TOTAL4 + f);
+                s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
+            }
+            store(f, s4);
+        }
     }
+    if (threadIdx.x == 0) C_MARK(10);
 }
 
 namespace {
-using CEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-CEncodeFn c_encode = nullptr;
 bool c_attr_set = false;
-
+int c_sms = 0;
 bool c_init() {
-    if (!c_encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult st;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st) != cudaSuccess ||
-            st != cudaDriverEntryPointSuccess || !fn)
-            return false;
-        c_encode = reinterpret_cast<CEncodeFn>(fn);
-    }
     if (!c_attr_set) {
         if (cudaFuncSetAttribute(tfy_conv3x3_fprop_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)FPROP_SMEM) != cudaSuccess ||
+                                 (int)FP_SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(tfy_conv3x3_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)DGRAD_SMEM) != cudaSuccess ||
+                                 (int)DG_SMEM) != cudaSuccess ||
             cudaFuncSetAttribute(tfy_conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)WGRAD_SMEM) != cudaSuccess)
+                                 (int)WG_SMEM) != cudaSuccess)
+            return false;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || c_sms <= 0)
             return false;
         c_attr_set = true;
     }
     return true;
 }
-
-// NHWC bf16 tensor [B, H, W, C] seen as {8 c, W, B, H, C/8}; box = {8, bw, 2, bh, C/8}
-bool c_map_nhwc(CUtensorMap* m, const void* p, int B, int H, int W, int C, int bw, int bh) {
-    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)B, (cuuint64_t)H, (cuuint64_t)(C / 8)};
-    cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)W * C * 2, 16};
-    cuuint32_t box[5] = {8, (cuuint32_t)bw, 2, (cuuint32_t)bh, (cuuint32_t)(C / 8)};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    return c_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-// weights [O][9][C] bf16 seen as {8 c, O, C/8, 9}; one box = everything, stored [tap][c group][o][8 c]
-bool c_map_w(CUtensorMap* m, const void* p) {
-    cuuint64_t dims[4] = {8, (cuuint64_t)COUT, (cuuint64_t)CG_IN, (cuuint64_t)TAPS};
-    cuuint64_t strides[3] = {(cuuint64_t)TAPS * CIN * 2, 16, (cuuint64_t)CIN * 2};
-    cuuint32_t box[4] = {8, (cuuint32_t)COUT, (cuuint32_t)CG_IN, (cuuint32_t)TAPS};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    return c_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+// persistent grid: one CTA per SM, trimmed so that the patches divide as evenly as possible
+int c_grid(int n_patches) {
+    if (n_patches <= c_sms) return n_patches;
+    const int waves = (n_patches + c_sms - 1) / c_sms;
+    return (n_patches + waves - 1) / waves;
 }
 }  // namespace
 
 extern "C" {
+
+// debug: device buffer of 16 x int64 per CTA receiving the event timeline of the next launches (nullptr = off)
+int tfy_conv_set_timeline(long long* buf) {
+    return (int)cudaMemcpyToSymbol(c_timeline, &buf, sizeof(buf));
+}
+
+// number of fp32 elements of the `partials` scratch buffer tfy_conv3x3_c32_wgrad needs
+size_t tfy_conv3x3_c32_wgrad_scratch_elems() { return (size_t)160 * WG_OUT; }
 
 // a: [B, H, W, 32] bf16 (NHWC), w: [64, 3, 3, 32] bf16, bias: [64] bf16
 // pooled / code: [B, (H-2)/2, (W-2)/2, 64].  Requires (H-2) % 8 == 0, (W-2) % 8 == 0, B % 2 == 0.
 int tfy_conv3x3_c32_pool_fwd(const void* a, const void* w, const void* bias, void* pooled, void* code, int B, int H,
                              int W, float drop_rate, uint32_t seed, const TfyOptHyper* hp, cudaStream_t s) {
     const int OH = H - 2, OW = W - 2;
-    if ((OH % 8) || (OW % 8) || (B % 2)) return -2;
+    if ((OH % 8) || (OW % 8) || (B % 2) || drop_rate < 0.f || drop_rate >= 1.f) return -2;
     if (!c_init()) return -4;
-    CUtensorMap ma, mw;
-    if (!c_map_nhwc(&ma, a, B, H, W, CIN, HALO, HALO) || !c_map_w(&mw, w)) return -6;
-    dim3 grid(OW / 8, OH / 8, B / 2);
-    tfy_conv3x3_fprop_pool_kernel<<<grid, CONV_THREADS, FPROP_SMEM, s>>>(
-        ma, mw, (const __nv_bfloat16*)bias, (__nv_bfloat16*)pooled, (uint8_t*)code, OH, OW, drop_rate, seed, hp);
+    const int tiles_x = OW / 8, tiles_y = OH / 8, n_patches = tiles_x * tiles_y * (B / 2);
+    tfy_conv3x3_fprop_pool_kernel<<<c_grid(n_patches), FP_THREADS, FP_SMEM, s>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, (__nv_bfloat16*)pooled,
+        (uint8_t*)code, H, W, tiles_x, tiles_y, n_patches, drop_rate, seed, hp);
     return (int)cudaGetLastError();
 }
 
@@ -549,30 +779,24 @@ int tfy_conv3x3_c32_dgrad(const void* dz, const void* w, const void* gate, void*
                           cudaStream_t s) {
     if (B % 2) return -2;
     if (!c_init()) return -4;
-    CUtensorMap mz, mw;
-    if (!c_map_nhwc(&mz, dz, B, H - 2, W - 2, COUT, HALO, HALO) || !c_map_w(&mw, w)) return -6;
-    dim3 grid((W + 7) / 8, (H + 7) / 8, B / 2);
-    tfy_conv3x3_dgrad_kernel<<<grid, CONV_THREADS, DGRAD_SMEM, s>>>(mz, mw, (const __nv_bfloat16*)gate,
-                                                                    (__nv_bfloat16*)dx, H, W);
+    const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8, n_patches = tiles_x * tiles_y * (B / 2);
+    tfy_conv3x3_dgrad_kernel<<<c_grid(n_patches), DG_THREADS, DG_SMEM, s>>>(
+        (const __nv_bfloat16*)dz, (const __nv_bfloat16*)w, (const __nv_bfloat16*)gate, (__nv_bfloat16*)dx, H, W,
+        tiles_x, tiles_y, n_patches);
     return (int)cudaGetLastError();
 }
 
 // a: [B, H, W, 32], dz: [B, H-2, W-2, 64], dw: [64, 3, 3, 32] bf16 (overwritten).
-// acc32: 64*288 floats, zero on entry and on exit; sync: 2 x uint32, zeroed once at allocation.
-int tfy_conv3x3_c32_wgrad(const void* a, const void* dz, float* acc32, void* dw, uint32_t* sync, int B, int H, int W,
+// partials: tfy_conv3x3_c32_wgrad_scratch_elems() floats of scratch; sync: 2 x uint32, zeroed once at allocation.
+int tfy_conv3x3_c32_wgrad(const void* a, const void* dz, float* partials, void* dw, uint32_t* sync, int B, int H, int W,
                           cudaStream_t s) {
     const int OH = H - 2, OW = W - 2;
     if ((OH % 8) || (OW % 8) || (B % 2)) return -2;
-    if (!c_init()) return -4;
-    CUtensorMap mz, ma;
-    if (!c_map_nhwc(&mz, dz, B, OH, OW, COUT, 8, 8) || !c_map_nhwc(&ma, a, B, H, W, CIN, HALO, HALO)) return -6;
+    if (!c_init() || c_sms > 160) return -4;
     const int tiles_x = OW / 8, tiles_y = OH / 8, n_patches = tiles_x * tiles_y * (B / 2);
-    int grid = n_patches < 148 ? n_patches : 148;
-    // an even split keeps every CTA on the same number of patches (576 patches -> 144 CTAs x 4)
-    for (int g = grid; g >= 96; --g)
-        if (n_patches % g == 0) { grid = g; break; }
-    tfy_conv3x3_wgrad_kernel<<<grid, CONV_THREADS, WGRAD_SMEM, s>>>(mz, ma, acc32, (__nv_bfloat16*)dw, sync, tiles_x,
-                                                                    tiles_y, n_patches);
+    tfy_conv3x3_wgrad_kernel<<<c_grid(n_patches), WG_THREADS, WG_SMEM, s>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)dz, partials, (__nv_bfloat16*)dw, sync, H, W, tiles_x, tiles_y,
+        n_patches);
     return (int)cudaGetLastError();
 }
 

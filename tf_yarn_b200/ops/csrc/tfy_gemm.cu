@@ -60,6 +60,14 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a converged warp: the compiler keeps descriptors in uniform registers and emits back-to-back
+// UTCHMMA / UTMALDG (with `lane == 0` each one was wrapped in an ELECT / R2UR / BRA.U.ANY loop, ~48 cycles).
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // K-major, 128-byte swizzled operand tile: rows of 64 bf16 (128 B); 8-row core groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -142,7 +150,7 @@ tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (tc_elect_one()) {
             for (int i = 0; i < n_kt; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (i / STAGES) & 1;
@@ -156,7 +164,7 @@ tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (tc_elect_one()) {
             const uint32_t idesc = make_idesc_bf16_m128(BN);
             for (int i = 0; i < n_kt; ++i) {
                 const int s = i % STAGES;

@@ -76,20 +76,22 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tfy_broadcast.argtypes = [ctxp, u64, sz, i, i, i, i, vp]
     lib.tfy_allgather.argtypes = [ctxp, u64, sz, i, i, vp]
     lib.tfy_fused_step.argtypes = [ctxp, i, i, i, i, u64, u64, sz, vp, vp, vp, vp, i, i, i, vp]
-    for name, args in _EXTRA_DECLS.items():
+    for name, (args, restype) in _EXTRA_DECLS.items():
         fn = getattr(lib, name, None)
         if fn is not None:
             fn.argtypes = args
+            fn.restype = restype
 
 
 # filled by other op modules (loss kernels, GEMM, PS) before the first load()
 _EXTRA_DECLS = {}
 
 
-def declare(name: str, argtypes) -> None:
-    _EXTRA_DECLS[name] = argtypes
+def declare(name: str, argtypes, restype=ctypes.c_int) -> None:
+    _EXTRA_DECLS[name] = (argtypes, restype)
     if _lib is not None and hasattr(_lib, name):
         getattr(_lib, name).argtypes = argtypes
+        getattr(_lib, name).restype = restype
 
 
 def load() -> ctypes.CDLL:
