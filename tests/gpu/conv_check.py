@@ -118,7 +118,7 @@ def main():
 
     # ---------------------------------------------------------------- wgrad
     acc = torch.full((int(lib.tfy_conv3x3_c32_wgrad_scratch_elems()),), float('nan'), dtype=torch.float32, device=dev)
-    sync = torch.zeros(2, dtype=torch.int32, device=dev)
+    sync = torch.zeros(192, dtype=torch.int32, device=dev)
     dw = torch.zeros(64, 3, 3, 32, dtype=bf16, device=dev)
     dw_ref = torch.nn.grad.conv2d_weight(a_nchw, (64, 32, 3, 3), dz.permute(0, 3, 1, 2).float()).permute(0, 2, 3, 1)
     for it in range(3):                      # repeated launches: accumulator re-zeroing and barrier reuse
@@ -126,8 +126,30 @@ def main():
                                        B, H, W, stream())
         torch.cuda.synchronize()
         report(f"wgrad_{it}", dw, dw_ref, 0.01)
-    res["wgrad_sync"] = {"ok": sync.tolist() == [0, 3], "sync": sync.tolist()}
-    print("wgrad rc", rc, "sync", sync.tolist())
+    res["wgrad_sync"] = {"ok": sync[:2].tolist() == [0, 3], "sync": sync[:4].tolist()}
+    print("wgrad rc", rc, "sync", sync[:4].tolist())
+
+    # ---------------------------------------------------------------- first-layer wgrad + bias grad (tensor core)
+    native.declare("tfy_conv3x3_c1_wgrad_tc", [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5
+                   + [ctypes.c_int] * 3 + [ctypes.c_void_p])
+    x1 = torch.rand(B, 28, 28, 1, device=dev)
+    dz1 = (torch.randn(B, 26, 26, 32, device=dev) * 0.5).to(bf16)
+    acc1 = torch.zeros(320, dtype=torch.float32, device=dev)
+    cnt1 = torch.zeros(1, dtype=torch.int32, device=dev)
+    dw1 = torch.zeros(32, 3, 3, 1, dtype=bf16, device=dev)
+    db1 = torch.zeros(32, dtype=bf16, device=dev)
+    x1b = x1.to(bf16).float()
+    dw1_ref = torch.nn.grad.conv2d_weight(x1b.permute(0, 3, 1, 2), (32, 1, 3, 3),
+                                          dz1.permute(0, 3, 1, 2).float()).permute(0, 2, 3, 1)
+    db1_ref = dz1.float().sum((0, 1, 2))
+    for it, (xt, f32) in enumerate([(x1, 1), (x1.to(bf16), 0), (x1, 1)]):
+        rc = lib.tfy_conv3x3_c1_wgrad_tc(xt.data_ptr(), f32, dz1.data_ptr(), acc1.data_ptr(), cnt1.data_ptr(),
+                                         dw1.data_ptr(), db1.data_ptr(), B, 28, 28, stream())
+        torch.cuda.synchronize()
+        report(f"c1_wgrad_tc_{it}", dw1, dw1_ref, 0.01)
+        report(f"c1_dbias_tc_{it}", db1, db1_ref, 0.01)
+    res["c1_state"] = {"ok": bool((acc1 == 0).all()) and int(cnt1.item()) == 0}
+    print("c1 rc", rc, "acc zero", bool((acc1 == 0).all()), "cnt", int(cnt1.item()))
 
     # ---------------------------------------------------------------- timings (hot L2; the in-graph numbers
     # come from profiles/launches_*.csv)
@@ -139,6 +161,9 @@ def main():
                                                                  dx.data_ptr(), B, H, W, stream()))
     t["wgrad_tc_us"] = timeit(lambda: lib.tfy_conv3x3_c32_wgrad(a.data_ptr(), dz.data_ptr(), acc.data_ptr(),
                                                                  dw.data_ptr(), sync.data_ptr(), B, H, W, stream()))
+    t["c1_wgrad_tc_us"] = timeit(lambda: lib.tfy_conv3x3_c1_wgrad_tc(
+        x1.data_ptr(), 1, dz1.data_ptr(), acc1.data_ptr(), cnt1.data_ptr(), dw1.data_ptr(), db1.data_ptr(), B, 28, 28,
+        stream()))
     wcl = w.permute(0, 3, 1, 2)
     acl = a.permute(0, 3, 1, 2)
     dzcl = dz.permute(0, 3, 1, 2)
@@ -156,13 +181,18 @@ def main():
                                                    stream()),
         "wgrad": lambda: lib.tfy_conv3x3_c32_wgrad(a.data_ptr(), dz.data_ptr(), acc.data_ptr(), dw.data_ptr(),
                                                    sync.data_ptr(), B, H, W, stream()),
+        "c1wgrad": lambda: lib.tfy_conv3x3_c1_wgrad_tc(x1.data_ptr(), 1, dz1.data_ptr(), acc1.data_ptr(),
+                                                       cnt1.data_ptr(), dw1.data_ptr(), db1.data_ptr(), B, 28, 28,
+                                                       stream()),
     }
     names = {"fprop": ["t0_ns", "setup", "prod_issued0", "prod_arrive0", "mma_full0", "mma_issued0", "epi_tfull0",
                        "epi_done0", "epi_tfull_last", "epi_done_last", "end", "mma_issued_last", "prod_done"],
              "dgrad": ["t0_ns", "setup", "prod_issued0", "prod_arrive0", "mma_full0", "mma_issued0", "epi_tfull0",
                        "-", "epi_tfull_last", "-", "end", "mma_issued_last", "prod_done"],
              "wgrad": ["t0_ns", "setup", "prod_issued0", "prod_arrive0", "mma_full0", "mma_issued_all", "epi_tmem_full",
-                       "partials_stored", "grid_barrier", "-", "end", "-", "prod_done"]}
+                       "partials_stored", "grid_barrier", "-", "end", "-", "prod_done"],
+             "c1wgrad": ["t0_ns", "setup", "built0", "built_last", "mma_full0", "mma_issued_all", "epi_tmem_full",
+                         "atomics_done", "counter_done", "-", "end"]}
     res["timeline"] = {}
     for k, fn in launches.items():
         for _ in range(3):

@@ -40,6 +40,7 @@ native.declare("tfy_conv3x3_c32_pool_fwd", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i,
 native.declare("tfy_conv3x3_c32_dgrad", [_vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad_scratch_elems", [], restype=ctypes.c_size_t)
+native.declare("tfy_conv3x3_c1_wgrad_tc", [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 
 PARTIAL_BLOCKS = 592
 
@@ -149,7 +150,9 @@ class FastSequentialEngine(GraphTrainEngine):
         self._hp = self.fused.hyper.data_ptr()
         self._k = 0
         self._acc32 = {}
-        self._conv_sync = torch.zeros(2, dtype=torch.int32, device=dev)     # grid barrier of the wgrad kernel
+        self._conv_sync = torch.zeros(192, dtype=torch.int32, device=dev)     # grid barrier of the wgrad kernel
+        self._c1_acc = torch.zeros(320, dtype=torch.float32, device=dev)    # first-layer dW/db accumulator
+        self._c1_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
 
     # ------------------------------------------------------------------ helpers
     def _s(self):
@@ -356,6 +359,16 @@ class FastSequentialEngine(GraphTrainEngine):
                 OH, OW = H - 2, W - 2
                 scale = 1.0 / (1.0 - st.drop) if st.drop > 0 else 1.0
                 gated, pre_gated = pre_gated, False
+                if (Cin == 1 and O == 32 and gated and not st.pool and aux is None and first
+                        and os.environ.get("TFY_NO_TC_CONV") != "1"):
+                    # first layer: dW and db in ONE tensor-core kernel (im2col built in shared memory)
+                    dz = grad if grad.is_contiguous() else grad.contiguous()
+                    self._chk(lib.tfy_conv3x3_c1_wgrad_tc(xin.data_ptr(), int(xin_f32), dz.data_ptr(),
+                                                          self._c1_acc.data_ptr(), self._c1_cnt.data_ptr(),
+                                                          w.grad.data_ptr(), b.grad.data_ptr(), B, H, W, s),
+                              "conv3x3_c1_wgrad_tc")
+                    grad = None
+                    continue
                 if st.pool:
                     dz = torch.empty((B, OH, OW, O), dtype=bf16, device=grad.device)
                     self._chk(lib.tfy_pool_drop_relu_bwd(grad.data_ptr(), aux.data_ptr(), dz.data_ptr(), scale, B, OH,
