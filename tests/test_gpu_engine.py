@@ -274,3 +274,55 @@ def test_tcgen05_conv_kernels_match_fp32_reference(batch, monkeypatch, tmp_path)
     monkeypatch.chdir(tmp_path)
     monkeypatch.setattr(sys, "argv", ["conv_check.py", str(batch)])
     assert mod.main() == 0, mod.res
+
+
+@pytest.mark.parametrize("B,K,C", [(128, 128, 10), (100, 256, 16), (37, 512, 3)])
+def test_fused_dense_head_matches_autograd(B, K, C):
+    """Fused classifier head (fwd + bwd + previous Dense gate/bias-grad) vs fp32 autograd of the same math."""
+    import ctypes
+    from tf_yarn_b200.keras import fastpath  # noqa: F401  (declares the kernel)
+    from tf_yarn_b200.ops import native
+    lib = native.load()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(B + K + C)
+    h = torch.randn(B, K, device=dev, generator=g).relu().bfloat16()
+    w2 = (torch.randn(C, K, device=dev, generator=g) * 0.2).bfloat16()
+    b2 = (torch.randn(C, device=dev, generator=g) * 0.1).bfloat16()
+    y = torch.randint(0, C, (B,), device=dev, generator=g)
+    mask = (torch.rand(B, K, device=dev, generator=g) > 0.4).to(torch.uint8)
+    scale = 2.0
+    loss = torch.zeros((), device=dev)
+    stats = torch.zeros(2, device=dev)
+    dw2 = torch.zeros(C, K, dtype=torch.bfloat16, device=dev)
+    db2 = torch.zeros(C, dtype=torch.bfloat16, device=dev)
+    dh = torch.zeros(B, K, dtype=torch.bfloat16, device=dev)
+    db1 = torch.zeros(K, dtype=torch.bfloat16, device=dev)
+    scratch = torch.zeros(int(lib.tfy_dense_head_scratch_elems(K, C)), device=dev)
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    # reference
+    hf = h.float().requires_grad_(True)
+    wf = w2.float().requires_grad_(True)
+    bf = b2.float().requires_grad_(True)
+    logits = hf @ wf.t() + bf
+    ref_loss = torch.nn.functional.cross_entropy(logits, y)
+    ref_loss.backward()
+    ref_dh = hf.grad * mask.float() * scale
+    for _ in range(2):      # twice: the scratch buffer and the counter must come back clean
+        rc = lib.tfy_dense_head_fused(h.data_ptr(), w2.data_ptr(), b2.data_ptr(), y.data_ptr(), mask.data_ptr(),
+                                      ctypes.c_float(scale), loss.data_ptr(), stats.data_ptr(), dw2.data_ptr(),
+                                      db2.data_ptr(), dh.data_ptr(), db1.data_ptr(), scratch.data_ptr(),
+                                      counter.data_ptr(), B, K, C, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+
+        def close(a, b, tol=0.02):
+            scale_ = b.abs().max().item() + 1e-6
+            assert (a.float() - b).abs().max().item() <= tol * scale_, ((a.float() - b).abs().max().item(), scale_)
+        assert abs(loss.item() - ref_loss.item()) < 1e-3 * max(1.0, abs(ref_loss.item()))
+        close(dw2, wf.grad)
+        close(db2, bf.grad)
+        close(dh, ref_dh)
+        close(db1, ref_dh.sum(0))
+        assert bool((scratch == 0).all()) and int(counter.item()) == 0
+    assert stats[1].item() == 2 * B
+    assert stats[0].item() == 2 * (logits.argmax(1) == y).sum().item()

@@ -41,6 +41,9 @@ native.declare("tfy_conv3x3_c32_dgrad", [_vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad_scratch_elems", [], restype=ctypes.c_size_t)
 native.declare("tfy_conv3x3_c1_wgrad_tc", [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
+native.declare("tfy_dense_head_scratch_elems", [_i, _i], restype=ctypes.c_size_t)
+native.declare("tfy_dense_head_fused", [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                        _vp])
 
 PARTIAL_BLOCKS = 592
 
@@ -150,8 +153,8 @@ class FastSequentialEngine(GraphTrainEngine):
         self._hp = self.fused.hyper.data_ptr()
         self._k = 0
         self._acc32 = {}
-        self._conv_sync = torch.zeros(192, dtype=torch.int32, device=dev)     # grid barrier of the wgrad kernel
-        self._c1_acc = torch.zeros(320, dtype=torch.float32, device=dev)    # first-layer dW/db accumulator
+        self._conv_sync = torch.zeros(1024, dtype=torch.int32, device=dev)     # grid barrier of the wgrad kernel
+        self._c1_acc = torch.zeros(16 * 320, dtype=torch.float32, device=dev)    # first-layer dW/db accumulator
         self._c1_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
 
     # ------------------------------------------------------------------ helpers
@@ -316,6 +319,28 @@ class FastSequentialEngine(GraphTrainEngine):
                 ly = st.layer
                 w, b = self._wb(ly)
                 xin = cur.to(bf16) if cur.dtype != bf16 else cur
+                prev = self.plan[li - 1] if li > 0 else None
+                K, C = xin.shape[1], ly.units
+                if (prev is not None and prev.kind == "dense" and K % 128 == 0 and K <= 512 and C <= 16
+                        and xin.is_contiguous() and os.environ.get("TFY_NO_FUSED_HEAD") != "1"):
+                    # one launch: logits, loss, dlogits, dW2, db2 and the gradient entering the previous Dense
+                    # layer (its ReLU / dropout gate and bias gradient included)
+                    pmask = saved[li - 1][1]
+                    pscale = 1.0 / (1.0 - prev.drop) if prev.drop > 0 else 1.0
+                    _, pb = self._wb(prev.layer)
+                    if "head_scratch" not in self._acc32:
+                        self._acc32["head_scratch"] = torch.zeros(
+                            int(lib.tfy_dense_head_scratch_elems(K, C)), dtype=torch.float32, device=cur.device)
+                        self._acc32["head_counter"] = torch.zeros(1, dtype=torch.int32, device=cur.device)
+                    dh = torch.empty((B, K), dtype=bf16, device=cur.device)
+                    self._chk(lib.tfy_dense_head_fused(
+                        xin.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                        pmask.data_ptr() if pmask is not None else None, pscale, self._loss.data_ptr(),
+                        self._stats.data_ptr() if self.metric_fns else None, w.grad.data_ptr(), b.grad.data_ptr(),
+                        dh.data_ptr(), pb.grad.data_ptr(), self._acc32["head_scratch"].data_ptr(),
+                        self._acc32["head_counter"].data_ptr(), B, K, C, s), "dense_head_fused")
+                    saved.append(("fused", dh))
+                    continue
                 logits = torch.mm(xin, w.t())
                 C = ly.units
                 dlogits = torch.empty((B, C), dtype=bf16, device=cur.device)
@@ -327,11 +352,15 @@ class FastSequentialEngine(GraphTrainEngine):
         # -------- backward
         grad = None
         pre_gated = False          # the dgrad kernel of the next layer already applied this layer's ReLU gate
+        dense_gated = False        # the fused head already produced the gated gradient + db of the Dense below
         for li in range(len(self.plan) - 1, -1, -1):
             st = self.plan[li]
             sv = saved[li]
             first = li == 0
-            if st.kind == "head":
+            if st.kind == "head" and sv[0] == "fused":
+                grad = sv[1]
+                dense_gated = True          # the Dense layer below already has its gated gradient and db
+            elif st.kind == "head":
                 xin, dlogits = sv
                 w, _ = self._wb(st.layer)
                 torch.mm(dlogits.t(), xin, out=w.grad)
@@ -341,10 +370,13 @@ class FastSequentialEngine(GraphTrainEngine):
                 ly = st.layer
                 w, b = self._wb(ly)
                 scale = 1.0 / (1.0 - st.drop) if st.drop > 0 else 1.0
-                self._chk(lib.tfy_act_drop_bwd_bias(grad.data_ptr(), mask.data_ptr() if mask is not None else None,
-                                                    None, grad.data_ptr(), scale, B, ly.units,
-                                                    self._partial.data_ptr(), b.grad.data_ptr(),
-                                                    self._counter.data_ptr(), s), "act_drop_bwd_bias")
+                if dense_gated:
+                    dense_gated = False
+                else:
+                    self._chk(lib.tfy_act_drop_bwd_bias(grad.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                                        None, grad.data_ptr(), scale, B, ly.units,
+                                                        self._partial.data_ptr(), b.grad.data_ptr(),
+                                                        self._counter.data_ptr(), s), "act_drop_bwd_bias")
                 torch.mm(grad.t(), xin, out=w.grad)
                 grad = torch.mm(grad, w) if not first else None
             elif st.kind == "flatten":

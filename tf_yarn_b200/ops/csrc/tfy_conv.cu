@@ -56,9 +56,7 @@ constexpr size_t DG_SMEM = (size_t)DG_STAGES * Z_HALO_B + W_BYTES + 1024 + 256;
 constexpr int WG_STAGES = 4, WG_STAGE_B = Z_PATCH_B + A_HALO_PAD;                         // 29696
 constexpr int WG_WORK_WARPS = 16, WG_THREADS = (WG_WORK_WARPS + 2) * 32;                   // 576
 constexpr int WG_OUT = COUT * TAPS * CIN;                                                 // 18432
-constexpr int WG_ROW_F = TAPS * CIN + 4;               // padded fp32 row of the staged partial tile (banks)
 constexpr size_t WG_SMEM = (size_t)WG_STAGES * WG_STAGE_B + 1024 + 256;
-static_assert((size_t)COUT * WG_ROW_F * 4 <= (size_t)WG_STAGES * WG_STAGE_B, "partial tile must fit in the ring");
 
 constexpr uint32_t SW128 = 2, SW64 = 4;                // UMMA descriptor layout types
 
@@ -503,8 +501,7 @@ tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
 // `partials[blockIdx.x]` (L2 resident); after a grid-wide arrive/release it reduces a slice of the 18432
 // outputs over all partials in a fixed order (deterministic, no atomics) and writes bf16 dW.
 // warps 0..15 epilogue + final reduction, warp 16 MMA, warp 17 TMA.
-// sync: 2 + 160 uint32, zero-initialised once: [1] = generation, [2 + cta] = per-CTA arrival flags (a single
-// arrival counter costs ~30 cycles per CTA of same-address atomic serialisation: 4.4k cycles for 144 CTAs).
+// sync: 1024 uint32, zero-initialised once (generation + two levels of arrival counters, see below).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_a,
@@ -515,16 +512,16 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
     uint8_t* stages = c_align1024(smem_raw);        // [4] { dz [8 h][2 n][8 w][128 B] sw128 ; a [10 h][2 n][10 w][64 B] sw64 }
     uint64_t* full = reinterpret_cast<uint64_t*>(stages + (size_t)WG_STAGES * WG_STAGE_B);
     uint64_t* empty = full + WG_STAGES;
-    uint64_t* tmem_full = empty + WG_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tap_full = empty + WG_STAGES;                         // [9]: accumulator of tap t is final
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tap_full + TAPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t gen0_s = *reinterpret_cast<volatile uint32_t*>(sync + 1);   // same value for every thread
+    const uint32_t gen0 = threadIdx.x == 0 ? *reinterpret_cast<volatile uint32_t*>(sync) : 0u;
     if (threadIdx.x == 0) {
         c_prefetch_map(&map_dz);
         c_prefetch_map(&map_a);
         for (int s = 0; s < WG_STAGES; ++s) { c_mbar_init(&full[s], 1); c_mbar_init(&empty[s], 1); }
-        c_mbar_init(tmem_full, 1);
+        for (int t = 0; t < TAPS; ++t) c_mbar_init(&tap_full[t], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WG_WORK_WARPS) c_tmem_alloc<512>(tmem_slot);
@@ -550,42 +547,47 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
         }
     } else if (warp == WG_WORK_WARPS) {
         if (c_elect_one()) {
+            // Patches are taken WG_STAGES at a time and the taps form the OUTER loop: the accumulator of tap t
+            // is final after the last group's pass over t, so its store overlaps the MMAs of taps t+1..8.
             const uint32_t idesc = c_idesc(64, CIN, 1, 1);
-            for (int i = 0; i < my_patches; ++i) {
-                const int s = i % WG_STAGES;
-                c_mbar_wait(&full[s], (i / WG_STAGES) & 1);
-                if (i == 0) C_MARK(4);
+            const int n_groups = (my_patches + WG_STAGES - 1) / WG_STAGES;
+            for (int g = 0; g < n_groups; ++g) {
+                const int cnt = min(WG_STAGES, my_patches - g * WG_STAGES);
+                for (int q = 0; q < cnt; ++q) c_mbar_wait(&full[q], g & 1);
+                if (g == 0) C_MARK(4);
                 c_fence_after();
-                const uint32_t dz0 = c_smem_u32(stages + (size_t)s * WG_STAGE_B), a0 = dz0 + Z_PATCH_B;
+                const uint32_t st0 = c_smem_u32(stages);
 #pragma unroll 1
                 for (int t = 0; t < TAPS; ++t) {
                     const int kh = t / 3, kw = t - kh * 3;
+#pragma unroll 1
+                    for (int q = 0; q < cnt; ++q) {
+                        const uint32_t dz0 = st0 + q * WG_STAGE_B, a0 = dz0 + Z_PATCH_B;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {          // 16 pixels (one h row of both images) per MMA
-                        // A = dz^T: M = 64 o inside the 128 B pixel row; K = pixels, 8-pixel groups 1024 B apart
-                        const uint64_t adesc = c_desc(dz0 + j * 2 * 8 * Z_PIX_B, 8 * Z_PIX_B, SW128);
-                        // B = a (tap shifted): N = 32 c inside the 64 B pixel row; K = pixels, groups = (h, n) rows
-                        const uint64_t bdesc = c_desc(a0 + (j + kh) * 2 * A_ROW_B + kw * A_PIX_B, A_ROW_B, SW64);
-                        c_umma(tmem_base + (uint32_t)(t * CIN), adesc, bdesc, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                        for (int j = 0; j < 8; ++j) {      // 16 pixels (one h row of both images) per MMA
+                            // A = dz^T: M = 64 o inside the 128 B pixel row; K = pixels, 8-pixel groups 1024 B apart
+                            const uint64_t adesc = c_desc(dz0 + j * 2 * 8 * Z_PIX_B, 8 * Z_PIX_B, SW128);
+                            // B = a (tap shifted): N = 32 c inside the 64 B pixel row; K = pixels, groups = (h, n) rows
+                            const uint64_t bdesc = c_desc(a0 + (j + kh) * 2 * A_ROW_B + kw * A_PIX_B, A_ROW_B, SW64);
+                            c_umma(tmem_base + (uint32_t)(t * CIN), adesc, bdesc, idesc, (g > 0 || q > 0 || j > 0) ? 1u : 0u);
+                        }
                     }
+                    if (g == n_groups - 1) c_commit(&tap_full[t]);
                 }
-                c_commit(&empty[s]);                        // smem stage reusable once these MMAs retire
+                for (int q = 0; q < cnt; ++q) c_commit(&empty[q]);     // stages reusable once these MMAs retire
             }
-            c_commit(tmem_full);
             C_MARK(5);
         }
     } else if (my_patches > 0) {
         // M = 64 accumulator: row o lives in TMEM lane (o % 16) + 32 * (o / 16): lanes 0..15 of each quadrant.
-        // Stage the tile as [64 o][288 + 4 pad] fp32 in the (now idle) ring -- warp = (quadrant, tap group) --
-        // then one bulk copy per row.
+        // warp = (quadrant, tap group): 16 lanes write the 128-byte (o, tap) rows of the fp32 partial tile.
         const int quad = warp & 3, tg = warp >> 2;                       // taps tg, tg+4, tg+8
-        float* tile = reinterpret_cast<float*>(stages);
-        c_mbar_wait(tmem_full, 0);
-        if (threadIdx.x == 0) C_MARK(6);
-        c_fence_after();
-        float* row = tile + (size_t)(quad * 16 + (lane & 15)) * WG_ROW_F;
+        float* mine = partials + (size_t)blockIdx.x * WG_OUT + (size_t)(quad * 16 + (lane & 15)) * (TAPS * CIN);
 #pragma unroll 1
         for (int t = tg; t < TAPS; t += 4) {
+            c_mbar_wait(&tap_full[t], 0);
+            if (threadIdx.x == 0 && t == 0) C_MARK(6);
+            c_fence_after();
             uint32_t acc[2][16];
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * CIN);
             c_tmem_ld16(taddr, acc[0]);
@@ -594,46 +596,45 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
             if (lane < 16) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<uint4*>(row + t * CIN + j) =
-                        make_uint4(acc[j >> 4][j & 15], acc[j >> 4][(j & 15) + 1], acc[j >> 4][(j & 15) + 2],
-                                   acc[j >> 4][(j & 15) + 3]);
+                    __stcg(reinterpret_cast<float4*>(mine + t * CIN + j),
+                           make_float4(__uint_as_float(acc[j >> 4][j & 15]), __uint_as_float(acc[j >> 4][(j & 15) + 1]),
+                                       __uint_as_float(acc[j >> 4][(j & 15) + 2]),
+                                       __uint_as_float(acc[j >> 4][(j & 15) + 3])));
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // smem writes -> bulk-copy engine
-        asm volatile("bar.sync 1, %0;" ::"r"(WG_WORK_WARPS * 32) : "memory");   // all 16 worker warps staged
-        if (warp < 4 && lane < 16) {
-            float* dst = partials + (size_t)blockIdx.x * WG_OUT + (size_t)(warp * 16 + lane) * (TAPS * CIN);
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                         "r"(c_smem_u32(tile + (size_t)(warp * 16 + lane) * WG_ROW_F)), "r"((uint32_t)(TAPS * CIN * 4))
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes complete before the arrive
-            __threadfence();
-        }
+        __threadfence();
     }
     c_fence_before();
     __syncthreads();
     if (warp == WG_WORK_WARPS) c_tmem_free<512>(tmem_base);
     if (threadIdx.x == 0) C_MARK(7);
 
-    // grid-wide arrive / release on per-CTA flags (all CTAs are co-resident: grid <= #SMs, one CTA per SM).
-    // gen0 cannot change before every CTA, this one included, has arrived.
-    {
-        uint32_t* flags = sync + 2;
-        const uint32_t target = gen0_s + 1;
-        if (threadIdx.x == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(target) : "memory");
-        }
-        if (threadIdx.x < gridDim.x) {
-            uint32_t v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
-            } while (v != target);
-        }
-        __syncthreads();
-        if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(sync + 1) = target;
+    // Grid-wide arrive / release (all CTAs are co-resident: grid <= #SMs, one CTA per SM).  Same-sector atomics
+    // serialise at ~20-30 cycles each and every returning atomic in a chain costs an L2 round trip, so: arrivals
+    // are fire-and-forget `red`s spread over 16 counters (one per 128-byte line, sync[32 + 32 k]); CTA 0 polls
+    // them, clears them and bumps the generation word sync[0] that everybody else polls.
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync + 32 + 32 * (blockIdx.x & 15u)) : "memory");
     }
+    if (blockIdx.x == 0 && warp == 0) {
+        if (lane < 16 && lane < (int)gridDim.x) {
+            const uint32_t expect = (gridDim.x - (uint32_t)lane + 15u) / 16u;
+            volatile uint32_t* cnt = sync + 32 + 32 * lane;
+            while (*cnt != expect) __nanosleep(20);
+            *cnt = 0u;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(sync) = gen0 + 1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile uint32_t*>(sync) == gen0) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
     if (threadIdx.x == 0) C_MARK(8);
     // slice of the outputs owned by this CTA (float4 units), summed over the partials in a fixed order
     constexpr int TOTAL4 = WG_OUT / 4;
@@ -662,7 +663,7 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
                 s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
             }
         }
-        red[threadIdx.x] = s4;                                       // (bulk copies drained before the barrier)
+        red[threadIdx.x] = s4;
         __syncthreads();
         if (part == 0) {
             for (int q = 1; q < parts; ++q) {
@@ -693,9 +694,10 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
 // shared memory by 128 threads from the tiny single-channel input.  Replaces the CUDA-core wgrad kernel
 // (28.8 us) and the separate bias-gradient column sum (8.2 us) of the first layer.
 // warps 0..3 build X~ (warp 0 also runs the epilogue), warp 4 MMA, warp 5 TMA.
-// acc: 320 floats [n][o], zero on entry, left zero; counter: one uint32, zero on entry, left zero.
+// acc: 16 replicas of 320 floats [n][o] (same-sector atomics serialise, so CTAs spread over replicas), zero on
+// entry, left zero; counter: one uint32, zero on entry, left zero.
 // ------------------------------------------------------------------------------------------------
-constexpr int C1_O = 32, C1_STAGES = 4, C1_PIX = 128;
+constexpr int C1_O = 32, C1_STAGES = 4, C1_PIX = 128, C1_REPLICAS = 16;
 constexpr int C1_A_B = C1_PIX * 128, C1_B_B = C1_PIX * 64, C1_STAGE_B = C1_A_B + C1_B_B;   // 16 KB + 8 KB
 constexpr int C1_THREADS = 192;
 constexpr size_t C1_SMEM = (size_t)C1_STAGES * C1_STAGE_B + 1024 + 256;
@@ -821,7 +823,8 @@ tfy_conv3x3_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const
             if (lane < 10) {
 #pragma unroll
                 for (int o = 0; o < C1_O; ++o)
-                    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(acc + lane * C1_O + o),
+                    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(acc + (blockIdx.x % C1_REPLICAS) * (10 * C1_O) +
+                                                                        lane * C1_O + o),
                                  "f"(__uint_as_float(d[o >> 4][o & 15]))
                                  : "memory");
             }
@@ -843,10 +846,14 @@ tfy_conv3x3_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const
         __threadfence();
         for (int i = threadIdx.x; i < 10 * C1_O; i += C1_THREADS) {
             const int n = i / C1_O, o = i - n * C1_O;
-            const float val = __ldcg(acc + i);
+            float val = 0.f;
+#pragma unroll
+            for (int rep = 0; rep < C1_REPLICAS; ++rep) {
+                val += __ldcg(acc + rep * (10 * C1_O) + i);
+                __stcg(acc + rep * (10 * C1_O) + i, 0.f);
+            }
             if (n < 9) dw[o * 9 + n] = __float2bfloat16(val);
             else dbias[o] = __float2bfloat16(val);
-            __stcg(acc + i, 0.f);
         }
         if (threadIdx.x == 0) *counter = 0u;
     }
@@ -954,7 +961,7 @@ int tfy_conv3x3_c32_dgrad(const void* dz, const void* w, const void* gate, void*
 }
 
 // a: [B, H, W, 32], dz: [B, H-2, W-2, 64], dw: [64, 3, 3, 32] bf16 (overwritten).
-// partials: tfy_conv3x3_c32_wgrad_scratch_elems() floats of scratch; sync: 2 x uint32, zeroed once at allocation.
+// partials: tfy_conv3x3_c32_wgrad_scratch_elems() floats of scratch; sync: 1024 x uint32, zeroed once at allocation.
 int tfy_conv3x3_c32_wgrad(const void* a, const void* dz, float* partials, void* dw, uint32_t* sync, int B, int H, int W,
                           cudaStream_t s) {
     const int OH = H - 2, OW = W - 2;
@@ -969,7 +976,7 @@ int tfy_conv3x3_c32_wgrad(const void* a, const void* dz, float* partials, void* 
 }
 
 // First-layer (C_in = 1, 32 filters) weight + bias gradient.  x: [B, H, W, 1] fp32 or bf16, dz: [B, H-2, W-2, 32] bf16
-// (already gated by the layer's ReLU), dw: [32, 3, 3, 1] bf16, dbias: [32] bf16.  acc: 320 floats and counter:
+// (already gated by the layer's ReLU), dw: [32, 3, 3, 1] bf16, dbias: [32] bf16.  acc: 16 x 320 floats and counter:
 // one uint32, both zero on entry (and left zero).
 int tfy_conv3x3_c1_wgrad_tc(const void* x, int x_is_f32, const void* dz, float* acc, uint32_t* counter, void* dw,
                             void* dbias, int B, int H, int W, cudaStream_t s) {
