@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256)
 tfy_fused_step_kernel(TfyCommCtx c, uint64_t grad_off, uint64_t param_off, size_t shard_n,
                       float* __restrict__ master, float* __restrict__ s1, float* __restrict__ s2,
                       TfyOptHyper* __restrict__ hp, int zero_grads) {
+    tfy_pdl_sync();
     using GP = TfyPack<GT>;
     using PP = TfyPack<PT>;
     constexpr int NG = 8 / GP::N;  // 16-byte packs per 8 gradient elements
@@ -366,7 +367,7 @@ int tfy_fused_step(const TfyCommCtx* c, int grad_dtype, int param_dtype, int opt
     if (grid <= 0) grid = tfy_pick_grid(shard_n / 8, block, mode == TFY_MODE_LOCAL ? 148 * 6 : 148 * 2);
     if (grid > TFY_MAX_BLOCKS) grid = TFY_MAX_BLOCKS;
 #define TFY_FS4(GT, PT, O, M)                                                                                  \
-    tfy_fused_step_kernel<GT, PT, O, M><<<grid, block, 0, s>>>(*c, grad_off, param_off, shard_n, master, s1, s2, \
+    tfy_launch_pdl((tfy_fused_step_kernel<GT, PT, O, M>), dim3(grid), dim3(block), 0, s, *c, grad_off, param_off, shard_n, master, s1, s2, \
                                                                 hp, zero_grads)
 #define TFY_FS3(GT, PT, O)                                   \
     do {                                                     \

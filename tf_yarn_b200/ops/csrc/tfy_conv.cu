@@ -239,6 +239,7 @@ tfy_conv3x3_fprop_pool_kernel(const __grid_constant__ CUtensorMap map_a, const _
     __syncthreads();
     c_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tfy_pdl_sync();                      // upstream grids complete; our dependents may start launching
     if (threadIdx.x == 0) C_MARK(1);
     const int my_patches = ((int)blockIdx.x < n_patches) ? (n_patches - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -397,6 +398,7 @@ tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
     __syncthreads();
     c_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tfy_pdl_sync();                      // upstream grids complete; our dependents may start launching
     if (threadIdx.x == 0) C_MARK(1);
     const int my_patches = ((int)blockIdx.x < n_patches) ? (n_patches - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -516,7 +518,6 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tap_full + TAPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t gen0 = threadIdx.x == 0 ? *reinterpret_cast<volatile uint32_t*>(sync) : 0u;
     if (threadIdx.x == 0) {
         c_prefetch_map(&map_dz);
         c_prefetch_map(&map_a);
@@ -529,7 +530,9 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
     __syncthreads();
     c_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tfy_pdl_sync();                      // upstream grids complete; our dependents may start launching
     if (threadIdx.x == 0) C_MARK(1);
+    const uint32_t gen0 = threadIdx.x == 0 ? *reinterpret_cast<volatile uint32_t*>(sync) : 0u;
     const int my_patches = ((int)blockIdx.x < n_patches) ? (n_patches - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == WG_WORK_WARPS + 1) {
@@ -740,6 +743,7 @@ tfy_conv3x3_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const
     __syncthreads();
     c_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tfy_pdl_sync();                      // upstream grids complete; our dependents may start launching
     if (threadIdx.x == 0) C_MARK(1);
     const int my_chunks = ((int)blockIdx.x < n_chunks) ? (n_chunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int OH = H - 2, OW = W - 2;
@@ -941,7 +945,7 @@ int tfy_conv3x3_c32_pool_fwd(const void* a, const void* w, const void* bias, voi
     CUtensorMap ma, mw;
     if (!c_map_nhwc(&ma, a, B, H, W, CIN, HALO, HALO) || !c_map_w(&mw, w)) return -6;
     const int tiles_x = OW / 8, tiles_y = OH / 8, n_patches = tiles_x * tiles_y * (B / 2);
-    tfy_conv3x3_fprop_pool_kernel<<<c_grid(n_patches), FP_THREADS, FP_SMEM, s>>>(
+    tfy_launch_pdl((tfy_conv3x3_fprop_pool_kernel), dim3(c_grid(n_patches)), dim3(FP_THREADS), FP_SMEM, s, 
         ma, mw, (const __nv_bfloat16*)bias, (__nv_bfloat16*)pooled, (uint8_t*)code, H, W, tiles_x, tiles_y, n_patches,
         drop_rate, seed, hp);
     return (int)cudaGetLastError();
@@ -955,7 +959,7 @@ int tfy_conv3x3_c32_dgrad(const void* dz, const void* w, const void* gate, void*
     CUtensorMap mz, mw;
     if (!c_map_nhwc(&mz, dz, B, H - 2, W - 2, COUT, HALO, HALO) || !c_map_w(&mw, w)) return -6;
     const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8, n_patches = tiles_x * tiles_y * (B / 2);
-    tfy_conv3x3_dgrad_kernel<<<c_grid(n_patches), DG_THREADS, DG_SMEM, s>>>(
+    tfy_launch_pdl((tfy_conv3x3_dgrad_kernel), dim3(c_grid(n_patches)), dim3(DG_THREADS), DG_SMEM, s, 
         mz, mw, (const __nv_bfloat16*)gate, (__nv_bfloat16*)dx, H, W, tiles_x, tiles_y, n_patches);
     return (int)cudaGetLastError();
 }
@@ -970,7 +974,7 @@ int tfy_conv3x3_c32_wgrad(const void* a, const void* dz, float* partials, void* 
     CUtensorMap mz, ma;
     if (!c_map_nhwc(&mz, dz, B, OH, OW, COUT, 8, 8) || !c_map_nhwc(&ma, a, B, H, W, CIN, HALO, HALO)) return -6;
     const int tiles_x = OW / 8, tiles_y = OH / 8, n_patches = tiles_x * tiles_y * (B / 2);
-    tfy_conv3x3_wgrad_kernel<<<c_grid(n_patches), WG_THREADS, WG_SMEM, s>>>(mz, ma, partials, (__nv_bfloat16*)dw, sync,
+    tfy_launch_pdl((tfy_conv3x3_wgrad_kernel), dim3(c_grid(n_patches)), dim3(WG_THREADS), WG_SMEM, s, mz, ma, partials, (__nv_bfloat16*)dw, sync,
                                                                             tiles_x, tiles_y, n_patches);
     return (int)cudaGetLastError();
 }
@@ -1006,10 +1010,10 @@ int tfy_conv3x3_c1_wgrad_tc(const void* x, int x_is_f32, const void* dz, float* 
     }
     const int grid = c_grid(n_chunks);
     if (x_is_f32)
-        tfy_conv3x3_c1_wgrad_tc_kernel<float><<<grid, C1_THREADS, C1_SMEM, s>>>(
+        tfy_launch_pdl((tfy_conv3x3_c1_wgrad_tc_kernel<float>), dim3(grid), dim3(C1_THREADS), C1_SMEM, s, 
             mz, (const float*)x, acc, counter, (__nv_bfloat16*)dw, (__nv_bfloat16*)dbias, H, W, n_pix, n_chunks);
     else
-        tfy_conv3x3_c1_wgrad_tc_kernel<__nv_bfloat16><<<grid, C1_THREADS, C1_SMEM, s>>>(
+        tfy_launch_pdl((tfy_conv3x3_c1_wgrad_tc_kernel<__nv_bfloat16>), dim3(grid), dim3(C1_THREADS), C1_SMEM, s, 
             mz, (const __nv_bfloat16*)x, acc, counter, (__nv_bfloat16*)dw, (__nv_bfloat16*)dbias, H, W, n_pix,
             n_chunks);
     return (int)cudaGetLastError();

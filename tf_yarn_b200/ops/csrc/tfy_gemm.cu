@@ -148,6 +148,7 @@ tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    tfy_pdl_sync();                      // upstream grids complete; our dependents may start launching
 
     if (warp == 0) {
         if (tc_elect_one()) {
@@ -305,7 +306,7 @@ int tfy_gemm_bf16(const void* A, const void* B, void* C, float* C32, const void*
     const int out_mode = (split_k > 1 || (C == nullptr && C32 != nullptr)) ? 1 : 0;
     if (out_mode == 1 && C32 == nullptr) return -7;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, split_k);
-    tfy_gemm_bf16_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, s>>>(ma, mb, (__nv_bfloat16*)C, C32,
+    tfy_launch_pdl((tfy_gemm_bf16_kernel), dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, s, ma, mb, (__nv_bfloat16*)C, C32,
                                                                 (const __nv_bfloat16*)bias, M, N, K, ldc, relu,
                                                                 out_mode, per);
     return (int)cudaGetLastError();

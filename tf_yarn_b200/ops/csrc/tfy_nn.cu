@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256)
 tfy_conv3x3_c1_fwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                           const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                           int O) {
+    tfy_pdl_sync();
     extern __shared__ float s_w[];  // [9][O] + [O] bias
     for (int i = threadIdx.x; i < 9 * O; i += blockDim.x) {
         const int o = i % O, t = i / O;
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(256)
 tfy_bias_act_drop_fwd_kernel(ZT* z, const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* y,
                              uint8_t* __restrict__ mask, size_t rows, int C, int relu, float drop_rate, uint32_t seed,
                              const TfyOptHyper* __restrict__ hp) {
+    tfy_pdl_sync();
     const int G = C / 8;
     const size_t total = rows * G;
     const uint32_t step = hp ? (uint32_t)hp->step : 0u;
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(256)
 tfy_act_drop_bwd_bias_kernel(const __nv_bfloat16* dy, const uint8_t* __restrict__ mask,
                              const __nv_bfloat16* __restrict__ y, __nv_bfloat16* dz, float scale, size_t rows, int C,
                              float* __restrict__ partial, __nv_bfloat16* __restrict__ dbias, uint32_t* counter) {
+    tfy_pdl_sync();
     extern __shared__ float s_sum[];  // [C]
     for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
     __syncthreads();
@@ -354,6 +357,7 @@ __global__ void __launch_bounds__(256)
 tfy_pool_drop_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dp, const uint8_t* __restrict__ code,
                               __nv_bfloat16* __restrict__ dz, float scale, int B, int H, int W, int C,
                               float* __restrict__ partial, __nv_bfloat16* __restrict__ dbias, uint32_t* counter) {
+    tfy_pdl_sync();
     extern __shared__ float s_sum[];
     for (int c = threadIdx.x; c < C; c += blockDim.x) s_sum[c] = 0.f;
     __syncthreads();
@@ -498,6 +502,7 @@ tfy_dense_head_fused_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bflo
                             __nv_bfloat16* __restrict__ db2, __nv_bfloat16* __restrict__ dh,
                             __nv_bfloat16* __restrict__ db1, float* __restrict__ scratch,
                             uint32_t* __restrict__ counter, int B, int K, int C) {
+    tfy_pdl_sync();
     extern __shared__ __align__(16) uint8_t head_smem[];
     const int KP = K + 8;                                           // padded row (bank spread)
     __nv_bfloat16* s_h = reinterpret_cast<__nv_bfloat16*>(head_smem);                 // [16][KP]
@@ -671,11 +676,11 @@ int tfy_conv3x3_c1_fwd(const void* x, int x_is_f32, const void* w, const void* b
     const int grid = tfy_grid_for(total, 256, 148 * 8);
     const size_t smem = (size_t)(10 * O) * sizeof(float);
     if (x_is_f32)
-        tfy_conv3x3_c1_fwd_kernel<float><<<grid, 256, smem, s>>>((const float*)x, (const __nv_bfloat16*)w,
+        tfy_launch_pdl((tfy_conv3x3_c1_fwd_kernel<float>), dim3(grid), dim3(256), smem, s, (const float*)x, (const __nv_bfloat16*)w,
                                                                   (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, B, H,
                                                                   W, O);
     else
-        tfy_conv3x3_c1_fwd_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(
+        tfy_launch_pdl((tfy_conv3x3_c1_fwd_kernel<__nv_bfloat16>), dim3(grid), dim3(256), smem, s, 
             (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, B, H, W, O);
     return (int)cudaGetLastError();
 }
@@ -697,7 +702,7 @@ int tfy_bias_act_drop_fwd(const void* z, const void* bias, void* y, void* mask, 
                           float drop_rate, uint32_t seed, const TfyOptHyper* hp, cudaStream_t s) {
     if (C % 8) return -2;
     const int grid = tfy_grid_for(rows * (C / 8), 256, 148 * 8);
-    tfy_bias_act_drop_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)z, (const __nv_bfloat16*)bias,
+    tfy_launch_pdl((tfy_bias_act_drop_fwd_kernel<__nv_bfloat16>), dim3(grid), dim3(256), 0, s, (__nv_bfloat16*)z, (const __nv_bfloat16*)bias,
                                                                      (__nv_bfloat16*)y, (uint8_t*)mask, rows, C, relu,
                                                                      drop_rate, seed, hp);
     return (int)cudaGetLastError();
@@ -708,7 +713,7 @@ int tfy_bias_act_drop_fwd_f32(void* z32, const void* bias, void* y, void* mask, 
                               float drop_rate, uint32_t seed, const TfyOptHyper* hp, cudaStream_t s) {
     if (C % 8) return -2;
     const int grid = tfy_grid_for(rows * (C / 8), 256, 148 * 8);
-    tfy_bias_act_drop_fwd_kernel<float><<<grid, 256, 0, s>>>((float*)z32, (const __nv_bfloat16*)bias,
+    tfy_launch_pdl((tfy_bias_act_drop_fwd_kernel<float>), dim3(grid), dim3(256), 0, s, (float*)z32, (const __nv_bfloat16*)bias,
                                                              (__nv_bfloat16*)y, (uint8_t*)mask, rows, C, relu,
                                                              drop_rate, seed, hp);
     return (int)cudaGetLastError();
@@ -720,7 +725,7 @@ int tfy_act_drop_bwd_bias(const void* dy, const void* mask, const void* y, void*
     int grid = tfy_grid_for(rows * (C / 8), 256, 592);
     // the kernel needs gridDim*blockDim >= C/8 so that every column group has a thread
     if ((size_t)grid * 256 < (size_t)(C / 8)) grid = (C / 8 + 255) / 256;
-    tfy_act_drop_bwd_bias_kernel<<<grid, 256, (C > 256 ? C : 256) * sizeof(float), s>>>(
+    tfy_launch_pdl((tfy_act_drop_bwd_bias_kernel), dim3(grid), dim3(256), (C > 256 ? C : 256) * sizeof(float), s, 
         (const __nv_bfloat16*)dy, (const uint8_t*)mask, (const __nv_bfloat16*)y, (__nv_bfloat16*)dz, scale, rows, C,
         partial, (__nv_bfloat16*)dbias, counter);
     return (int)cudaGetLastError();
@@ -742,7 +747,7 @@ int tfy_pool_drop_relu_bwd(const void* dp, const void* code, void* dz, float sca
     if (C % 8 || H % 2 || W % 2) return -2;
     const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
     int grid = tfy_grid_for(total, 256, 592);
-    tfy_pool_drop_relu_bwd_kernel<<<grid, 256, (C > 256 ? C : 256) * sizeof(float), s>>>(
+    tfy_launch_pdl((tfy_pool_drop_relu_bwd_kernel), dim3(grid), dim3(256), (C > 256 ? C : 256) * sizeof(float), s, 
         (const __nv_bfloat16*)dp, (const uint8_t*)code, (__nv_bfloat16*)dz, scale, B, H, W, C, partial,
         (__nv_bfloat16*)dbias, counter);
     return (int)cudaGetLastError();
@@ -776,7 +781,7 @@ int tfy_dense_head_fused(const void* h, const void* w2, const void* b2, const vo
         configured = true;
     }
     const int grid = (B + HEAD_ROWS - 1) / HEAD_ROWS;
-    tfy_dense_head_fused_kernel<<<grid, HEAD_THREADS, smem, s>>>(
+    tfy_launch_pdl((tfy_dense_head_fused_kernel), dim3(grid), dim3(HEAD_THREADS), smem, s, 
         (const __nv_bfloat16*)h, (const __nv_bfloat16*)w2, (const __nv_bfloat16*)b2, (const long long*)labels,
         (const uint8_t*)mask1, scale1, loss, stats, (__nv_bfloat16*)dw2, (__nv_bfloat16*)db2, (__nv_bfloat16*)dh,
         (__nv_bfloat16*)db1, scratch, counter, B, K, C);
