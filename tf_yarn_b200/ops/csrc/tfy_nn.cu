@@ -489,11 +489,19 @@ tfy_softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfl
 // One CTA per 16 rows; the batch reductions (dW2, db2, db1, loss) meet in an fp32 scratch buffer and the
 // last CTA to finish converts and clears it.
 // h: [B, K] bf16, W2: [C, K] bf16, b2: [C] bf16, labels: [B] int64, mask1: [B, K] uint8 (bit 0 = gradient
-// flows) or null.  K % 128 == 0, K <= 512, C <= 16.
+// flows) or null.  K in {128, 256, 512}, C <= 16.
 // scratch: [C*K | 16 | K | 2] floats, zero on entry and on exit; counter: one uint32, same.
 // ---------------------------------------------------------------------------------------------
+// debug: per-CTA event timeline of the head kernel (16 slots of SM-clock deltas per CTA), see tfy_nn_set_timeline
+__device__ long long* n_timeline = nullptr;
+#define N_MARK(k)                                                                    \
+    do {                                                                             \
+        if (n_tl && threadIdx.x == 0) n_tl[(size_t)blockIdx.x * 16 + (k)] = clock64() - n_t0; \
+    } while (0)
+
 constexpr int HEAD_THREADS = 256, HEAD_CMAX = 16, HEAD_ROWS = 16;
 
+template <int K>
 __global__ void __launch_bounds__(HEAD_THREADS)
 tfy_dense_head_fused_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ w2,
                             const __nv_bfloat16* __restrict__ b2, const long long* __restrict__ labels,
@@ -501,16 +509,21 @@ tfy_dense_head_fused_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bflo
                             float* __restrict__ stats, __nv_bfloat16* __restrict__ dw2,
                             __nv_bfloat16* __restrict__ db2, __nv_bfloat16* __restrict__ dh,
                             __nv_bfloat16* __restrict__ db1, float* __restrict__ scratch,
-                            uint32_t* __restrict__ counter, int B, int K, int C) {
+                            uint32_t* __restrict__ counter, int B, int C) {
+    // K is a template parameter: every loop that waits on global memory has a constant trip count and is
+    // fully unrolled, so its loads are issued back to back (the first version had ~18 serialised L2 round
+    // trips in five-iteration loops: 15 us for 0.5 MFLOP).
     tfy_pdl_sync();
+    long long* const n_tl = n_timeline;
+    const long long n_t0 = clock64();
     extern __shared__ __align__(16) uint8_t head_smem[];
-    const int KP = K + 8;                                           // padded row (bank spread)
+    constexpr int KP = K + 8;                                       // padded row (bank spread)
     __nv_bfloat16* s_h = reinterpret_cast<__nv_bfloat16*>(head_smem);                 // [16][KP]
-    float* s_w = reinterpret_cast<float*>(head_smem + (size_t)HEAD_ROWS * KP * 2);    // [C][K]
-    float* s_dl = s_w + (size_t)C * K;                                                // [16][HEAD_CMAX]
+    float* s_w = reinterpret_cast<float*>(head_smem + (size_t)HEAD_ROWS * KP * 2);    // [16][K], rows >= C are zero
+    float* s_dl = s_w + (size_t)HEAD_CMAX * K;                                                // [16][HEAD_CMAX]
     float* s_b = s_dl + HEAD_ROWS * HEAD_CMAX;                                        // [HEAD_CMAX]
     float* s_red = s_b + HEAD_CMAX;                                                   // loss, correct
-    float* s_col = s_red + 2;                                                         // [K]
+    float* s_col = s_red + 4;                                                         // [max(K, 256)], 16-byte aligned
     __shared__ uint32_t s_last;
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * HEAD_ROWS;
@@ -527,77 +540,126 @@ tfy_dense_head_fused_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bflo
         *reinterpret_cast<uint4*>(s_h + (size_t)r * KP + g * 8) =
             r < rows ? tfy_ld16(h + (size_t)(row0 + r) * K + g * 8) : make_uint4(0, 0, 0, 0);
     }
-    for (int i = tid; i < C * K; i += HEAD_THREADS) s_w[i] = bf16_to_f(w2[i]);
-    for (int i = tid; i < K; i += HEAD_THREADS) s_col[i] = 0.f;
+    {
+        constexpr int WV = HEAD_CMAX * K / 8 / HEAD_THREADS;        // 16-byte packs of W2 per thread (upper bound)
+        uint4 wv[WV];
+#pragma unroll
+        for (int q = 0; q < WV; ++q) {
+            const int i = tid + q * HEAD_THREADS;
+            wv[q] = i < C * K / 8 ? tfy_ld16(w2 + (size_t)i * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < WV; ++q) {                          // packs beyond C*K/8 were loaded as zeros
+            const int i = tid + q * HEAD_THREADS;
+            TfyPack<__nv_bfloat16>::unpack(wv[q], s_w + (size_t)i * 8);
+        }
+    }
     if (tid < HEAD_CMAX) s_b[tid] = (tid < C && b2) ? bf16_to_f(b2[tid]) : 0.f;
     if (tid < 2) s_red[tid] = 0.f;
     for (int i = tid; i < HEAD_ROWS * HEAD_CMAX; i += HEAD_THREADS) s_dl[i] = 0.f;
     __syncthreads();
 
+    N_MARK(1);
     // ---- B/C: logits (16 threads per row), softmax, loss, dlogits
     const float invB = 1.f / (float)B;
     {
-        const int r = tid >> 4, part = tid & 15, kq = K / 16;
-        float acc[HEAD_CMAX];
-#pragma unroll
-        for (int c = 0; c < HEAD_CMAX; ++c) acc[c] = 0.f;
+        // Classes are padded to 16 with zero weights (no per-class branches) and taken 4 at a time in a ROLLED
+        // loop: this code runs once per launch on 8 warps, so it is instruction-fetch bound -- the fully
+        // unrolled version (2400 instructions) spent 7k cycles here, mostly waiting for the I-cache.
+        const int r = tid >> 4, part = tid & 15;
+        constexpr int kq = K / 16;
+        const int lab = r < rows ? (int)labels[row0 + r] : -1;     // issued early: used after the GEMV
         const __nv_bfloat16* hr = s_h + (size_t)r * KP + part * kq;
-        for (int k = 0; k < kq; k += 8) {
-            float hv[8];
-            TfyPack<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(hr + k), hv);
+        float* s_logit = s_col;                                     // [16][16] scratch (s_col is used later)
+#pragma unroll 1
+        for (int cb = 0; cb < HEAD_CMAX; cb += 4) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int k = 0; k < kq; k += 8) {
+                float hv[8];
+                TfyPack<__nv_bfloat16>::unpack(*reinterpret_cast<const uint4*>(hr + k), hv);
 #pragma unroll
-            for (int c = 0; c < HEAD_CMAX; ++c) {
-                if (c < C) {
-                    const float* wr = s_w + (size_t)c * K + part * kq + k;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[c] = fmaf(hv[j], wr[j], acc[c]);
+                for (int c = 0; c < 4; ++c) {
+                    const float* wp = s_w + (size_t)(cb + c) * K + part * kq + k;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wp);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+                    acc[c] = fmaf(hv[0], w0.x, acc[c]); acc[c] = fmaf(hv[1], w0.y, acc[c]);
+                    acc[c] = fmaf(hv[2], w0.z, acc[c]); acc[c] = fmaf(hv[3], w0.w, acc[c]);
+                    acc[c] = fmaf(hv[4], w1.x, acc[c]); acc[c] = fmaf(hv[5], w1.y, acc[c]);
+                    acc[c] = fmaf(hv[6], w1.z, acc[c]); acc[c] = fmaf(hv[7], w1.w, acc[c]);
                 }
             }
+#pragma unroll
+            for (int off = 1; off < 16; off <<= 1) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+            }
+            if (part == 0) *reinterpret_cast<float4*>(s_logit + r * HEAD_CMAX + cb) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
+        __syncwarp();
+        // softmax / cross-entropy with one lane per class (the 16 lanes of a row group): a handful of shuffle
+        // steps instead of three serial 10-iteration loops on one lane per row
+        {
+            const int c = part;
+            const bool live = c < C && r < rows;
+            const float v = live ? s_logit[r * HEAD_CMAX + c] + s_b[c] : -3.0e38f;
+            float mx = v;
+            int amax = c;
 #pragma unroll
-        for (int c = 0; c < HEAD_CMAX; ++c) {
+            for (int off = 1; off < 16; off <<= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, mx, off);
+                const int oa = __shfl_xor_sync(0xffffffffu, amax, off);
+                if (ov > mx || (ov == mx && oa < amax)) { mx = ov; amax = oa; }
+            }
+            const float e = live ? __expf(v - mx) : 0.f;
+            float se = e;
 #pragma unroll
-            for (int off = 1; off < 16; off <<= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
-        }
-        if (part == 0 && r < rows) {
-            float mx = -3.0e38f;
-            int amax = 0;
+            for (int off = 1; off < 16; off <<= 1) se += __shfl_xor_sync(0xffffffffu, se, off);
+            const bool hit = live && c == lab;
+            if (live) s_dl[r * HEAD_CMAX + c] = (e / se - (hit ? 1.f : 0.f)) * invB;
+            float my_loss = hit ? (mx + __logf(se)) - v : 0.f;
+            float my_correct = (hit && amax == lab) ? 1.f : 0.f;
 #pragma unroll
-            for (int c = 0; c < HEAD_CMAX; ++c)
-                if (c < C) {
-                    acc[c] += s_b[c];
-                    if (acc[c] > mx) { mx = acc[c]; amax = c; }
-                }
-            float se = 0.f;
-#pragma unroll
-            for (int c = 0; c < HEAD_CMAX; ++c)
-                if (c < C) se += __expf(acc[c] - mx);
-            const float lse = mx + __logf(se), inv_se = 1.f / se;
-            const int lab = (int)labels[row0 + r];
-            float my_loss = 0.f;
-#pragma unroll
-            for (int c = 0; c < HEAD_CMAX; ++c)
-                if (c < C) {
-                    s_dl[r * HEAD_CMAX + c] = (__expf(acc[c] - mx) * inv_se - (c == lab ? 1.f : 0.f)) * invB;
-                    if (c == lab) my_loss = lse - acc[c];
-                }
-            atomicAdd(&s_red[0], my_loss);
-            atomicAdd(&s_red[1], (amax == lab) ? 1.f : 0.f);
+            for (int off = 16; off > 0; off >>= 1) {
+                my_loss += __shfl_xor_sync(0xffffffffu, my_loss, off);
+                my_correct += __shfl_xor_sync(0xffffffffu, my_correct, off);
+            }
+            if ((tid & 31) == 0) {
+                atomicAdd(&s_red[0], my_loss);
+                atomicAdd(&s_red[1], my_correct);
+            }
         }
     }
+    __syncthreads();
+    for (int i = tid; i < K; i += HEAD_THREADS) s_col[i] = 0.f;     // s_logit scratch -> column sums
     __syncthreads();
     if (tid == 0) {
         atomicAdd(g_red, s_red[0]);
         atomicAdd(g_red + 1, s_red[1]);
     }
 
+    N_MARK(2);
     // ---- D: partial dW2[c][k] = sum_r dl[r][c] h[r][k]; db2[c] = sum_r dl[r][c]
-    for (int idx = tid; idx < C * K; idx += HEAD_THREADS) {
-        const int c = idx / K, k = idx - c * K;
-        float a = 0.f;
+    {
+        // a thread keeps one column k of h (16 values) in registers and runs over the classes it owns
+        constexpr int KREP = K >= HEAD_THREADS ? K / HEAD_THREADS : 1;
+        constexpr int CSTEP = K >= HEAD_THREADS ? 1 : HEAD_THREADS / K;
 #pragma unroll
-        for (int r = 0; r < HEAD_ROWS; ++r) a = fmaf(s_dl[r * HEAD_CMAX + c], bf16_to_f(s_h[(size_t)r * KP + k]), a);
-        atomicAdd(g_dw + idx, a);
+        for (int kr = 0; kr < KREP; ++kr) {
+            const int k = (K >= HEAD_THREADS) ? tid + kr * HEAD_THREADS : tid % K;
+            float hc[HEAD_ROWS];
+#pragma unroll
+            for (int r = 0; r < HEAD_ROWS; ++r) hc[r] = bf16_to_f(s_h[(size_t)r * KP + k]);
+#pragma unroll 1
+            for (int cc = 0; cc < HEAD_CMAX / CSTEP; ++cc) {
+                const int c = cc * CSTEP + ((K >= HEAD_THREADS) ? 0 : tid / K);
+                if (c >= C) break;
+                float a = 0.f;
+#pragma unroll
+                for (int r = 0; r < HEAD_ROWS; ++r) a = fmaf(s_dl[r * HEAD_CMAX + c], hc[r], a);
+                if (c < C) atomicAdd(g_dw + (size_t)c * K + k, a);
+            }
+        }
     }
     if (tid < C) {
         float a = 0.f;
@@ -606,18 +668,44 @@ tfy_dense_head_fused_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bflo
         atomicAdd(g_db2 + tid, a);
     }
 
+    N_MARK(3);
     // ---- E: dh[r][k] = (sum_c dl[r][c] W2[c][k]) * gate * scale; db1[k] = sum_r dh[r][k]
     if (dh) {
-        for (int idx = tid; idx < rows * K; idx += HEAD_THREADS) {
-            const int r = idx / K, k = idx - r * K;
-            float v = 0.f;
+        // a thread keeps one column k of W2 (16 classes) in registers and runs over the rows it owns
+        constexpr int KREP = K >= HEAD_THREADS ? K / HEAD_THREADS : 1;
+        constexpr int RSTEP = K >= HEAD_THREADS ? 1 : HEAD_THREADS / K;
 #pragma unroll
-            for (int c = 0; c < HEAD_CMAX; ++c)
-                if (c < C) v = fmaf(s_dl[r * HEAD_CMAX + c], s_w[(size_t)c * K + k], v);
-            const size_t g = (size_t)(row0 + r) * K + k;
-            if (mask1) v = (mask1[g] & 1) ? v * scale1 : 0.f;
-            dh[g] = __float2bfloat16(v);
-            if (db1) atomicAdd(&s_col[k], v);
+        for (int kr = 0; kr < KREP; ++kr) {
+            const int k = (K >= HEAD_THREADS) ? tid + kr * HEAD_THREADS : tid % K;
+            const int rbase = (K >= HEAD_THREADS) ? 0 : tid / K;
+            float wk[HEAD_CMAX];
+#pragma unroll
+            for (int c = 0; c < HEAD_CMAX; ++c) wk[c] = s_w[(size_t)c * K + k];
+            uint32_t mkbits = 0;                                    // gate bits of the rows this thread owns
+#pragma unroll
+            for (int j = 0; j < HEAD_ROWS / RSTEP; ++j) {
+                const int r = rbase + j * RSTEP;
+                const uint32_t bit = (mask1 && r < rows) ? (uint32_t)(mask1[(size_t)(row0 + r) * K + k] & 1) : 1u;
+                mkbits |= bit << j;
+            }
+            float col = 0.f;
+#pragma unroll 2
+            for (int j = 0; j < HEAD_ROWS / RSTEP; ++j) {
+                const int r = rbase + j * RSTEP;
+                float v = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < HEAD_CMAX; c4 += 4) {
+                    const float4 d = *reinterpret_cast<const float4*>(s_dl + r * HEAD_CMAX + c4);
+                    v = fmaf(d.x, wk[c4], v); v = fmaf(d.y, wk[c4 + 1], v);
+                    v = fmaf(d.z, wk[c4 + 2], v); v = fmaf(d.w, wk[c4 + 3], v);
+                }
+                if (mask1) v = ((mkbits >> j) & 1u) ? v * scale1 : 0.f;
+                if (r < rows) {
+                    dh[(size_t)(row0 + r) * K + k] = __float2bfloat16(v);
+                    col += v;
+                }
+            }
+            if (db1) atomicAdd(&s_col[k], col);
         }
         if (db1) {
             __syncthreads();
@@ -625,16 +713,36 @@ tfy_dense_head_fused_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bflo
         }
     }
 
+    N_MARK(4);
     // ---- the last CTA converts the batch sums and clears the scratch buffer
     __threadfence();
     __syncthreads();
+    N_MARK(5);
     if (tid == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
+    N_MARK(6);
     if (s_last) {
         __threadfence();
-        for (int i = tid; i < C * K; i += HEAD_THREADS) {
-            dw2[i] = __float2bfloat16(__ldcg(g_dw + i));
-            __stcg(g_dw + i, 0.f);
+        {
+            constexpr int FV = HEAD_CMAX * K / 4 / HEAD_THREADS;    // float4 packs per thread (upper bound)
+            float4 fv[FV];
+#pragma unroll
+            for (int q = 0; q < FV; ++q) {
+                const int i = tid + q * HEAD_THREADS;
+                fv[q] = i < C * K / 4 ? __ldcg(reinterpret_cast<const float4*>(g_dw) + i) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int q = 0; q < FV; ++q) {
+                const int i = tid + q * HEAD_THREADS;
+                if (i < C * K / 4) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(fv[q].x, fv[q].y), hi = __floats2bfloat162_rn(fv[q].z, fv[q].w);
+                    uint2 packed;
+                    packed.x = *reinterpret_cast<uint32_t*>(&lo);
+                    packed.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(dw2 + (size_t)i * 4) = packed;
+                    __stcg(reinterpret_cast<float4*>(g_dw) + i, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+            }
         }
         if (tid < HEAD_CMAX) {
             if (tid < C && db2) db2[tid] = __float2bfloat16(__ldcg(g_db2 + tid));
@@ -652,6 +760,7 @@ tfy_dense_head_fused_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bflo
             *counter = 0u;
         }
     }
+    N_MARK(7);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -763,6 +872,8 @@ int tfy_softmax_xent(const void* logits, const void* bias, const void* labels, f
     return (int)cudaGetLastError();
 }
 
+int tfy_nn_set_timeline(long long* buf) { return (int)cudaMemcpyToSymbol(n_timeline, &buf, sizeof(buf)); }
+
 // fused classifier head (forward + backward); returns -2 when the shape is outside the kernel's envelope.
 // scratch: tfy_dense_head_scratch_elems(K, C) floats and counter: one uint32, zero on entry (left zero).
 size_t tfy_dense_head_scratch_elems(int K, int C) { return (size_t)C * K + HEAD_CMAX + K + 2; }
@@ -770,21 +881,28 @@ size_t tfy_dense_head_scratch_elems(int K, int C) { return (size_t)C * K + HEAD_
 int tfy_dense_head_fused(const void* h, const void* w2, const void* b2, const void* labels, const void* mask1,
                          float scale1, float* loss, float* stats, void* dw2, void* db2, void* dh, void* db1,
                          float* scratch, uint32_t* counter, int B, int K, int C, cudaStream_t s) {
-    if (K % 128 || K > 512 || C < 1 || C > HEAD_CMAX || B < 1) return -2;
+    if (!(K == 128 || K == 256 || K == 512) || C < 1 || C > HEAD_CMAX || B < 1) return -2;
     const size_t smem = (size_t)HEAD_ROWS * (K + 8) * 2 +
-                        ((size_t)C * K + HEAD_ROWS * HEAD_CMAX + HEAD_CMAX + 2 + K) * 4;
-    static bool configured = false;
-    if (smem > 48 * 1024 && !configured) {
-        if (cudaFuncSetAttribute(tfy_dense_head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) !=
-            cudaSuccess)
-            return -5;
-        configured = true;
-    }
+                        ((size_t)HEAD_CMAX * K + HEAD_ROWS * HEAD_CMAX + HEAD_CMAX + 4 + (K > 256 ? K : 256)) * 4;
     const int grid = (B + HEAD_ROWS - 1) / HEAD_ROWS;
-    tfy_launch_pdl((tfy_dense_head_fused_kernel), dim3(grid), dim3(HEAD_THREADS), smem, s, 
-        (const __nv_bfloat16*)h, (const __nv_bfloat16*)w2, (const __nv_bfloat16*)b2, (const long long*)labels,
-        (const uint8_t*)mask1, scale1, loss, stats, (__nv_bfloat16*)dw2, (__nv_bfloat16*)db2, (__nv_bfloat16*)dh,
-        (__nv_bfloat16*)db1, scratch, counter, B, K, C);
+#define TFY_HEAD(KK)                                                                                                   \
+    do {                                                                                                               \
+        static bool configured = false;                                                                                \
+        if (smem > 48 * 1024 && !configured) {                                                                         \
+            if (cudaFuncSetAttribute(tfy_dense_head_fused_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     96 * 1024) != cudaSuccess)                                                        \
+                return -5;                                                                                             \
+            configured = true;                                                                                         \
+        }                                                                                                              \
+        tfy_launch_pdl((tfy_dense_head_fused_kernel<KK>), dim3(grid), dim3(HEAD_THREADS), smem, s,                     \
+                       (const __nv_bfloat16*)h, (const __nv_bfloat16*)w2, (const __nv_bfloat16*)b2,                    \
+                       (const long long*)labels, (const uint8_t*)mask1, scale1, loss, stats, (__nv_bfloat16*)dw2,      \
+                       (__nv_bfloat16*)db2, (__nv_bfloat16*)dh, (__nv_bfloat16*)db1, scratch, counter, B, C);          \
+    } while (0)
+    if (K == 128) TFY_HEAD(128);
+    else if (K == 256) TFY_HEAD(256);
+    else TFY_HEAD(512);
+#undef TFY_HEAD
     return (int)cudaGetLastError();
 }
 

@@ -4,7 +4,7 @@
 set -euo pipefail
 OUT=gpurun_out
 mkdir -p $OUT
-ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv \
     --log-file $OUT/launches.csv python tests/gpu/profile_step.py
 for K in tfy_gemm_bf16_kernel tfy_fused_step_kernel tfy_conv3x3_c1_wgrad_kernel tfy_pool_drop_relu_bwd_kernel; do
   PROFILE_STEPS=1 ncu --set full --clock-control none --import-source on --profile-from-start off \
