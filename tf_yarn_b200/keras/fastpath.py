@@ -139,6 +139,9 @@ class FastSequentialEngine(GraphTrainEngine):
         super().__init__(*args, **kwargs)
         self.plan = plan
         self.lib = native.load()
+        # every gradient element is overwritten by the plan's kernels each step (no accumulation), so the
+        # fused optimizer step does not have to clear the gradient buffer behind itself
+        self.fused.zero_grads = False
         dev = self.device
         width = 8
         for st in plan:
