@@ -208,16 +208,24 @@ def run_ours(args):
     value = world * PER_GPU_BATCH / (ms_per_step * 1e-3)
 
     # ---- end-to-end region: model.fit with per-step H2D (pinned) + per-step loss D2H ----------
-    n_e2e = args.steps * PER_GPU_BATCH
-    off = (warm % POOL_BATCHES) * PER_GPU_BATCH
-    if off + n_e2e > x_host.shape[0]:
-        off = 0
-    n_e2e = min(n_e2e, x_host.shape[0] - off)
-    e2e_steps = n_e2e // PER_GPU_BATCH
-    xe, ye = x_host[off:off + n_e2e], y_host[off:off + n_e2e]
+    # exactly K steps through the public API, fed by an iterable that walks the pinned host pool
+    class _HostPool:
+        cardinality = None
+
+        def __init__(self, first_batch):
+            self.b = first_batch
+
+        def __iter__(self):
+            while True:
+                b = self.b
+                self.b = (b + 1) % POOL_BATCHES
+                yield (x_host[b * PER_GPU_BATCH:(b + 1) * PER_GPU_BATCH],
+                       y_host[b * PER_GPU_BATCH:(b + 1) * PER_GPU_BATCH])
+
+    e2e_steps = args.steps
     _barrier(world)
     t0 = time.perf_counter()
-    hist = model.fit(xe, ye, batch_size=PER_GPU_BATCH, epochs=1, shuffle=False, verbose=0)
+    hist = model.fit(_HostPool(warm % POOL_BATCHES), steps_per_epoch=e2e_steps, epochs=1, verbose=0)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     _barrier(world)

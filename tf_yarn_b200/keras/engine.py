@@ -202,9 +202,10 @@ class GraphTrainEngine:
 
     def _capture(self, x, y) -> None:
         self.net.train()
-        self._static_x = _clone_struct(x)
-        self._static_y = _clone_struct(y)
+        # two input slots, and one captured graph per slot reading it in place: the copy stream fills slot
+        # (i+1) % 2 while graph[i % 2] runs, and no staging -> static copy sits in front of every step
         self._staging = [(_clone_struct(x), _clone_struct(y)) for _ in range(2)]
+        self._static_x, self._static_y = self._staging[0]
         fused = self.fused
         snap = (fused.master.clone(), fused.s1.clone(), fused.s2.clone(), fused.flat_params.clone(),
                 fused.hyper.clone(), self._metric_acc.clone())
@@ -213,6 +214,7 @@ class GraphTrainEngine:
             for _ in range(3):
                 self._forward_backward(self._static_x, self._static_y)
         self.stream.synchronize()
+        self.graphs = [None, None]
         if self.use_graph:
             # a CUDAGraph of an older engine being garbage-collected while this stream captures would
             # invalidate the capture (cudaGraphExecDestroy is not allowed then): collect now, pause GC
@@ -221,9 +223,15 @@ class GraphTrainEngine:
             was_enabled = gc.isenabled()
             gc.disable()
             try:
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph, stream=self.stream):
-                    self._forward_backward(self._static_x, self._static_y)
+                for slot in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    sx, sy = self._staging[slot]
+                    # the graphs never run concurrently (same stream), so they share one memory pool
+                    pool = self.graphs[0].pool() if slot else None
+                    with torch.cuda.graph(g, stream=self.stream, pool=pool):
+                        self._forward_backward(sx, sy)
+                    self.graphs[slot] = g
+                self.graph = self.graphs[0]
             finally:
                 if was_enabled:
                     gc.enable()
@@ -268,17 +276,13 @@ class GraphTrainEngine:
         sx, sy = self._staging[slot]
         self.stream.wait_event(ready)
         with torch.cuda.stream(self.stream):
-            _copy_struct(self._static_x, sx)
-            _copy_struct(self._static_y, sy)
-            free = torch.cuda.Event()
-            free.record(self.stream)
-            self._slot_free[slot] = free
             if self.graph is not None:
-                self.graph.replay()
+                self.graphs[slot].replay()
             else:
-                self._forward_backward(self._static_x, self._static_y)
+                self._forward_backward(sx, sy)
             done = torch.cuda.Event()
             done.record(self.stream)
+            self._slot_free[slot] = done          # the slot may be refilled once this step has run
         self.kernel_launches += self._launches_per_step
         return done
 
