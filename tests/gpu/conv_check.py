@@ -130,6 +130,39 @@ def main():
     res["wgrad_sync"] = {"ok": sv == [3, 0, 0], "sync": sv}
     print("wgrad rc", rc, "sync", sv)
 
+    # ---------------------------------------------------------------- fused un-pool variants vs the 3-kernel path
+    native.declare("tfy_conv3x3_c32_dgrad_unpool", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float]
+                   + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p])
+    native.declare("tfy_conv3x3_c32_wgrad_unpool", [ctypes.c_void_p] * 3 + [ctypes.c_float] + [ctypes.c_void_p] * 4
+                   + [ctypes.c_int] * 3 + [ctypes.c_void_p])
+    dp = (torch.randn(B, 12, 12, 64, device=dev) * 0.5).to(bf16)
+    scale_u = 1.0 / 0.75
+    dzp = torch.zeros(B, 24, 24, 64, dtype=bf16, device=dev)
+    partial_u = torch.zeros(592 * 9 * 64, dtype=torch.float32, device=dev)
+    cnt_u = torch.zeros(1, dtype=torch.int32, device=dev)
+    db_ref = torch.zeros(64, dtype=bf16, device=dev)
+    rc = lib.tfy_pool_drop_relu_bwd(dp.data_ptr(), c2.data_ptr(), dzp.data_ptr(), ctypes.c_float(scale_u), B, 24, 24,
+                                    64, partial_u.data_ptr(), db_ref.data_ptr(), cnt_u.data_ptr(), stream())
+    dw_a = torch.zeros(64, 3, 3, 32, dtype=bf16, device=dev)
+    dw_b = torch.zeros(64, 3, 3, 32, dtype=bf16, device=dev)
+    db_b = torch.zeros(64, dtype=bf16, device=dev)
+    dx_a = torch.zeros(B, H, W, 32, dtype=bf16, device=dev)
+    dx_b = torch.zeros(B, H, W, 32, dtype=bf16, device=dev)
+    lib.tfy_conv3x3_c32_wgrad(a.data_ptr(), dzp.data_ptr(), acc.data_ptr(), dw_a.data_ptr(), sync.data_ptr(), B, H, W,
+                              stream())
+    lib.tfy_conv3x3_c32_dgrad(dzp.data_ptr(), w.data_ptr(), a.data_ptr(), dx_a.data_ptr(), B, H, W, stream())
+    for it in range(2):
+        rc1 = lib.tfy_conv3x3_c32_wgrad_unpool(a.data_ptr(), dp.data_ptr(), c2.data_ptr(), ctypes.c_float(scale_u),
+                                               acc.data_ptr(), dw_b.data_ptr(), db_b.data_ptr(), sync.data_ptr(), B, H,
+                                               W, stream())
+        rc2 = lib.tfy_conv3x3_c32_dgrad_unpool(dp.data_ptr(), c2.data_ptr(), ctypes.c_float(scale_u), w.data_ptr(),
+                                               a.data_ptr(), dx_b.data_ptr(), B, H, W, stream())
+        torch.cuda.synchronize()
+        print("unpool rc", rc, rc1, rc2)
+        report(f"wgrad_unpool_{it}", dw_b, dw_a.float(), 0.004)
+        report(f"dbias_unpool_{it}", db_b, db_ref.float(), 0.01)
+        report(f"dgrad_unpool_{it}", dx_b, dx_a.float(), 0.004)
+
     # ---------------------------------------------------------------- first-layer wgrad + bias grad (tensor core)
     native.declare("tfy_conv3x3_c1_wgrad_tc", [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5
                    + [ctypes.c_int] * 3 + [ctypes.c_void_p])
@@ -165,6 +198,15 @@ def main():
     t["c1_wgrad_tc_us"] = timeit(lambda: lib.tfy_conv3x3_c1_wgrad_tc(
         x1.data_ptr(), 1, dz1.data_ptr(), acc1.data_ptr(), cnt1.data_ptr(), dw1.data_ptr(), db1.data_ptr(), B, 28, 28,
         stream()))
+    t["wgrad_unpool_us"] = timeit(lambda: lib.tfy_conv3x3_c32_wgrad_unpool(
+        a.data_ptr(), dp.data_ptr(), c2.data_ptr(), ctypes.c_float(scale_u), acc.data_ptr(), dw_b.data_ptr(),
+        db_b.data_ptr(), sync.data_ptr(), B, H, W, stream()))
+    t["dgrad_unpool_us"] = timeit(lambda: lib.tfy_conv3x3_c32_dgrad_unpool(
+        dp.data_ptr(), c2.data_ptr(), ctypes.c_float(scale_u), w.data_ptr(), a.data_ptr(), dx_b.data_ptr(), B, H, W,
+        stream()))
+    t["pool_bwd_us"] = timeit(lambda: lib.tfy_pool_drop_relu_bwd(
+        dp.data_ptr(), c2.data_ptr(), dzp.data_ptr(), ctypes.c_float(scale_u), B, 24, 24, 64, partial_u.data_ptr(),
+        db_ref.data_ptr(), cnt_u.data_ptr(), stream()))
     wcl = w.permute(0, 3, 1, 2)
     acl = a.permute(0, 3, 1, 2)
     dzcl = dz.permute(0, 3, 1, 2)

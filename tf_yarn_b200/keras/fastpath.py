@@ -41,6 +41,8 @@ native.declare("tfy_conv3x3_c32_dgrad", [_vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad_scratch_elems", [], restype=ctypes.c_size_t)
 native.declare("tfy_conv3x3_c1_wgrad_tc", [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
+native.declare("tfy_conv3x3_c32_dgrad_unpool", [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp])
+native.declare("tfy_conv3x3_c32_wgrad_unpool", [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_dense_head_scratch_elems", [_i, _i], restype=ctypes.c_size_t)
 native.declare("tfy_dense_head_fused", [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
                                         _vp])
@@ -419,6 +421,29 @@ class FastSequentialEngine(GraphTrainEngine):
                                                           w.grad.data_ptr(), b.grad.data_ptr(), B, H, W, s),
                               "conv3x3_c1_wgrad_tc")
                     grad = None
+                    continue
+                if (st.pool and self._tc_conv(st, B) and grad.is_contiguous()
+                        and os.environ.get("TFY_NO_UNPOOL_FUSION") != "1"):
+                    # pool/dropout/ReLU backward fused into the operand producers of wgrad and dgrad: the
+                    # 4x larger dz tensor is never written; db comes out of the wgrad kernel
+                    if "wgrad_scratch" not in self._acc32:
+                        self._acc32["wgrad_scratch"] = torch.empty(
+                            int(lib.tfy_conv3x3_c32_wgrad_scratch_elems()), dtype=torch.float32, device=grad.device)
+                    self._chk(lib.tfy_conv3x3_c32_wgrad_unpool(
+                        xin.data_ptr(), grad.data_ptr(), aux.data_ptr(), scale,
+                        self._acc32["wgrad_scratch"].data_ptr(), w.grad.data_ptr(), b.grad.data_ptr(),
+                        self._conv_sync.data_ptr(), B, H, W, s), "conv3x3_c32_wgrad_unpool")
+                    dp = grad
+                    grad = None
+                    if not first:
+                        prev = self.plan[li - 1]
+                        fold = (prev.kind == "conv" and prev.relu and not prev.pool and prev.drop == 0
+                                and saved[li - 1][2] is not None and saved[li - 1][2].data_ptr() == xin.data_ptr())
+                        grad = torch.empty((B, H, W, Cin), dtype=bf16, device=dp.device)
+                        self._chk(lib.tfy_conv3x3_c32_dgrad_unpool(
+                            dp.data_ptr(), aux.data_ptr(), scale, w.data_ptr(), xin.data_ptr() if fold else None,
+                            grad.data_ptr(), B, H, W, s), "conv3x3_c32_dgrad_unpool")
+                        pre_gated = fold
                     continue
                 if st.pool:
                     dz = torch.empty((B, OH, OW, O), dtype=bf16, device=grad.device)

@@ -51,12 +51,13 @@ constexpr int W_BYTES = TAPS * W_TAP_B;                // 36864
 
 constexpr int FP_STAGES = 3, FP_EPI_WARPS = 16, FP_THREADS = (FP_EPI_WARPS + 2) * 32;     // 576
 constexpr size_t FP_SMEM = (size_t)FP_STAGES * A_HALO_PAD + W_BYTES + 1024 + 256;
-constexpr int DG_STAGES = 3, DG_EPI_WARPS = 4, DG_THREADS = (DG_EPI_WARPS + 2) * 32;      // 192
+constexpr int DG_STAGES = 3, DG_EPI_WARPS = 4, DG_THREADS = (DG_EPI_WARPS + 2 + 4) * 32;  // 320: +4 un-pool producer warps
 constexpr size_t DG_SMEM = (size_t)DG_STAGES * Z_HALO_B + W_BYTES + 1024 + 256;
 constexpr int WG_STAGES = 4, WG_STAGE_B = Z_PATCH_B + A_HALO_PAD;                         // 29696
 constexpr int WG_WORK_WARPS = 16, WG_THREADS = (WG_WORK_WARPS + 2) * 32;                   // 576
 constexpr int WG_OUT = COUT * TAPS * CIN;                                                 // 18432
-constexpr size_t WG_SMEM = (size_t)WG_STAGES * WG_STAGE_B + 1024 + 256;
+constexpr int WG_PART = WG_OUT + COUT;                 // per-CTA partial: dW tile + db (un-pool variant)
+constexpr size_t WG_SMEM = (size_t)WG_STAGES * WG_STAGE_B + 1024 + 512 + WG_WORK_WARPS * COUT * 4;
 
 constexpr uint32_t SW128 = 2, SW64 = 4;                // UMMA descriptor layout types
 
@@ -201,6 +202,49 @@ struct CPatchIter {
         bz += sb;
     }
 };
+
+// Un-pooling producer task: the gradient dp of ONE pooled pixel (8 channels of group g) becomes the 2x2 window
+// of dz rows it came from, written straight into a swizzled [pixel rows][128 B] operand tile:
+//   dz[2py+dy, 2px+dx, o] = (code[o] & 4) && (code[o] & 3) == dy*2+dx ? dp[o] * scale : 0
+// (code byte of the forward kernel: argmax position + gate).  The fused pool/dropout/ReLU backward never
+// writes the 4x larger dz tensor to memory.  row0 = tile row of the window's top-left pixel, row_dy = rows per
+// image row of the tile (2 images interleaved: 2 * pixels per row).  Returns the gated values for db.
+struct CUnpoolIn {
+    uint4 v;
+    uint2 cd;
+};
+__device__ __forceinline__ CUnpoolIn c_unpool_load(const __nv_bfloat16* __restrict__ dp,
+                                                   const uint8_t* __restrict__ code, bool valid, size_t pidx, int g) {
+    CUnpoolIn in;
+    in.v = make_uint4(0, 0, 0, 0);
+    in.cd = make_uint2(0, 0);
+    if (valid) {
+        in.v = tfy_ld16(dp + pidx * COUT + g * 8);
+        in.cd = *reinterpret_cast<const uint2*>(code + pidx * COUT + g * 8);
+    }
+    return in;
+}
+__device__ __forceinline__ void c_unpool_emit(uint8_t* tile, const CUnpoolIn& in, float scale, int g, int row0,
+                                              int row_dy, float* gated) {
+    float f[8];
+    TfyPack<__nv_bfloat16>::unpack(in.v, f);
+    uint32_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        c[k] = ((k < 4 ? in.cd.x >> (8 * k) : in.cd.y >> (8 * (k - 4)))) & 0xffu;
+        f[k] = (c[k] & 4u) ? f[k] * scale : 0.f;
+        gated[k] = f[k];
+    }
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = ((c[k] & 3u) == (uint32_t)pos) ? f[k] : 0.f;
+        const int row = row0 + (pos >> 1) * row_dy + (pos & 1);
+        *reinterpret_cast<uint4*>(tile + (size_t)row * Z_PIX_B + ((uint32_t)(g ^ (row & 7)) << 4)) =
+            TfyPack<__nv_bfloat16>::pack(o);
+    }
+}
 
 }  // namespace
 
@@ -369,10 +413,14 @@ tfy_conv3x3_fprop_pool_kernel(const __grid_constant__ CUtensorMap map_a, const _
 // the previous layer's ReLU (gate = that layer's output: dx is zeroed where gate <= 0).
 // dz: [B, H-2, W-2, 64]; dx: [B, H, W, 32].  warps 0..3 epilogue, warp 4 MMA, warp 5 TMA (zero-fills the halo)
 // ------------------------------------------------------------------------------------------------
+// UNPOOL: the A operand is not loaded from a materialised dz but rebuilt by warps 6..9 from the pooled gradient
+// dp [B, (H-2)/2, (W-2)/2, 64] and the forward kernel's code bytes (c_unpool_task).
+template <bool UNPOOL>
 __global__ void __launch_bounds__(DG_THREADS, 1)
 tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_w,
                          const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ dx, int H, int W,
-                         int tiles_x, int tiles_y, int n_patches) {
+                         int tiles_x, int tiles_y, int n_patches, const __nv_bfloat16* __restrict__ dp,
+                         const uint8_t* __restrict__ code, float scale) {
     extern __shared__ uint8_t smem_raw[];
     C_TIMELINE_BEGIN();
     uint8_t* stages = c_align1024(smem_raw);                      // [3][10 h][2 n][10 w][128 B], 128B swizzle
@@ -386,9 +434,9 @@ tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        c_prefetch_map(&map_dz);
+        if (!UNPOOL) c_prefetch_map(&map_dz);
         c_prefetch_map(&map_w);
-        for (int s = 0; s < DG_STAGES; ++s) { c_mbar_init(&full[s], 1); c_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < DG_STAGES; ++s) { c_mbar_init(&full[s], UNPOOL ? 128 : 1); c_mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { c_mbar_init(&tfull[b], 1); c_mbar_init(&tempty[b], DG_EPI_WARPS * 32); }
         c_mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -407,7 +455,7 @@ tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
             c_mbar_expect_tx(wfull, W_BYTES);
             c_tma_3d(&map_w, wfull, w_tile, 0, 0, 0);
             CPatchIter it(tiles_x, tiles_y);
-            for (int i = 0; i < my_patches; ++i, it.next()) {
+            for (int i = 0; !UNPOOL && i < my_patches; ++i, it.next()) {
                 const int s = i % DG_STAGES;
                 if (i >= DG_STAGES) c_mbar_wait(&empty[s], ((i / DG_STAGES) - 1) & 1);
                 c_mbar_expect_tx(&full[s], Z_HALO_B);
@@ -424,6 +472,7 @@ tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
             for (int i = 0; i < my_patches; ++i) {
                 const int s = i % DG_STAGES, b = i & 1;
                 c_mbar_wait(&full[s], (i / DG_STAGES) & 1);
+                if (UNPOOL) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 if (i == 0) C_MARK(4);
                 if (i >= 2) c_mbar_wait(&tempty[b], ((i >> 1) - 1) & 1);
                 c_fence_after();
@@ -445,6 +494,41 @@ tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
                 c_commit(&tfull[b]);
                 if (i == 0) C_MARK(5);
                 if (i == my_patches - 1) C_MARK(11);
+            }
+        }
+    } else if (warp > DG_EPI_WARPS + 1) {
+        // ---------------- un-pool producers (UNPOOL only): 5 x 5 pooled pixels x 2 images x 8 channel groups
+        if (UNPOOL) {
+            const int ptid = threadIdx.x - (DG_EPI_WARPS + 2) * 32;           // 0..127
+            const int PH = (H - 2) / 2, PWp = (W - 2) / 2;
+            CPatchIter it(tiles_x, tiles_y);
+            for (int i = 0; i < my_patches; ++i, it.next()) {
+                const int s = i % DG_STAGES;
+                if (i >= DG_STAGES) c_mbar_wait(&empty[s], ((i / DG_STAGES) - 1) & 1);
+                uint8_t* tile = stages + (size_t)s * Z_HALO_B;
+                // 400 tasks per patch, 4 slots per thread: all loads are issued before the first is consumed
+                // (one L2 round trip per patch instead of four)
+                CUnpoolIn in[4];
+                int row0[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = ptid + u * 128;
+                    const int g = t & 7, n = (t >> 3) & 1, pp = min(t >> 4, 24);
+                    const int ppy = pp / 5, ppx = pp - ppy * 5;
+                    const int py = it.ty * 4 - 1 + ppy, px = it.tx * 4 - 1 + ppx;
+                    const bool valid = t < 400 && (unsigned)py < (unsigned)PH && (unsigned)px < (unsigned)PWp;
+                    const size_t pidx = ((size_t)(it.bz * 2 + n) * PH + (valid ? py : 0)) * PWp + (valid ? px : 0);
+                    in[u] = c_unpool_load(dp, code, valid, pidx, g);
+                    row0[u] = (ppy * 2 * 2 + n) * HALO + ppx * 2;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = ptid + u * 128;
+                    float gated[8];
+                    if (t < 400) c_unpool_emit(tile, in[u], scale, t & 7, row0[u], 2 * HALO, gated);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                c_mbar_arrive(&full[s]);
             }
         }
     } else {
@@ -505,10 +589,15 @@ tfy_conv3x3_dgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
 // warps 0..15 epilogue + final reduction, warp 16 MMA, warp 17 TMA.
 // sync: 1024 uint32, zero-initialised once (generation + two levels of arrival counters, see below).
 // ------------------------------------------------------------------------------------------------
+// UNPOOL: dz tiles are rebuilt by warps 0..3 from the pooled gradient dp and the forward kernel's code bytes
+// (c_unpool_task) and the bias gradient db = sum of the gated dp rides along as 64 more outputs.
+template <bool UNPOOL>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __grid_constant__ CUtensorMap map_a,
                          float* __restrict__ partials, __nv_bfloat16* __restrict__ dw, uint32_t* __restrict__ sync,
-                         int tiles_x, int tiles_y, int n_patches) {
+                         int tiles_x, int tiles_y, int n_patches, const __nv_bfloat16* __restrict__ dp,
+                         const uint8_t* __restrict__ code, float scale, __nv_bfloat16* __restrict__ db, int PH,
+                         int PWp) {
     extern __shared__ uint8_t smem_raw[];
     C_TIMELINE_BEGIN();
     uint8_t* stages = c_align1024(smem_raw);        // [4] { dz [8 h][2 n][8 w][128 B] sw128 ; a [10 h][2 n][10 w][64 B] sw64 }
@@ -516,12 +605,13 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
     uint64_t* empty = full + WG_STAGES;
     uint64_t* tap_full = empty + WG_STAGES;                         // [9]: accumulator of tap t is final
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tap_full + TAPS);
+    float* s_db = reinterpret_cast<float*>(tmem_slot + 4);          // [16 warps][64] bias-gradient partials (UNPOOL)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        c_prefetch_map(&map_dz);
+        if (!UNPOOL) c_prefetch_map(&map_dz);
         c_prefetch_map(&map_a);
-        for (int s = 0; s < WG_STAGES; ++s) { c_mbar_init(&full[s], 1); c_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < WG_STAGES; ++s) { c_mbar_init(&full[s], UNPOOL ? 257 : 1); c_mbar_init(&empty[s], 1); }
         for (int t = 0; t < TAPS; ++t) c_mbar_init(&tap_full[t], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -542,8 +632,8 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
                 const int s = i % WG_STAGES;
                 if (i >= WG_STAGES) c_mbar_wait(&empty[s], ((i / WG_STAGES) - 1) & 1);
                 uint8_t* st = stages + (size_t)s * WG_STAGE_B;
-                c_mbar_expect_tx(&full[s], Z_PATCH_B + A_HALO_B);
-                c_tma_4d(&map_dz, &full[s], st, 0, it.tx * 8, it.bz * 2, it.ty * 8);
+                c_mbar_expect_tx(&full[s], (UNPOOL ? 0 : Z_PATCH_B) + A_HALO_B);
+                if (!UNPOOL) c_tma_4d(&map_dz, &full[s], st, 0, it.tx * 8, it.bz * 2, it.ty * 8);
                 c_tma_4d(&map_a, &full[s], st + Z_PATCH_B, 0, it.tx * 8, it.bz * 2, it.ty * 8);
                 if (i == 0) C_MARK(2);
             }
@@ -557,6 +647,7 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
             for (int g = 0; g < n_groups; ++g) {
                 const int cnt = min(WG_STAGES, my_patches - g * WG_STAGES);
                 for (int q = 0; q < cnt; ++q) c_mbar_wait(&full[q], g & 1);
+                if (UNPOOL) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 if (g == 0) C_MARK(4);
                 c_fence_after();
                 const uint32_t st0 = c_smem_u32(stages);
@@ -582,10 +673,63 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
             C_MARK(5);
         }
     } else if (my_patches > 0) {
+        if (UNPOOL) {
+            // ---------------- un-pool producers (all 16 worker warps): a patch needs 4 x 4 pooled pixels x 2 images
+            // x 8 channel groups = 256 tasks; thread t serves task t & 255 of patches (t >> 8), (t >> 8) + 2, ...
+            // and always the same channel group, so db accumulates in registers.  Loads of two patches are in
+            // flight together.
+            const int t = threadIdx.x, task = t & 255, g = task & 7, n = (task >> 3) & 1, pp = task >> 4;
+            const int ppy = pp >> 2, ppx = pp & 3;
+            const int row0 = (ppy * 2 * 2 + n) * 8 + ppx * 2;
+            float colacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            CPatchIter it(tiles_x, tiles_y);
+            if (t >> 8) it.next();
+            for (int i = (t >> 8); i < my_patches; i += 4) {
+                // patches i and i + 2 (if any)
+                CPatchIter it2 = it;
+                it2.next(); it2.next();
+                const bool two = i + 2 < my_patches;
+                const size_t p0 = ((size_t)(it.bz * 2 + n) * PH + it.ty * 4 + ppy) * PWp + it.tx * 4 + ppx;
+                const size_t p1 = ((size_t)(it2.bz * 2 + n) * PH + it2.ty * 4 + ppy) * PWp + it2.tx * 4 + ppx;
+                const CUnpoolIn in0 = c_unpool_load(dp, code, true, p0, g);
+                const CUnpoolIn in1 = c_unpool_load(dp, code, two, two ? p1 : p0, g);
+                float gated[8];
+                {
+                    const int s = i % WG_STAGES;
+                    if (i >= WG_STAGES) c_mbar_wait(&empty[s], ((i / WG_STAGES) - 1) & 1);
+                    c_unpool_emit(stages + (size_t)s * WG_STAGE_B, in0, scale, g, row0, 16, gated);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) colacc[k] += gated[k];
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    c_mbar_arrive(&full[s]);
+                }
+                if (two) {
+                    const int i2 = i + 2, s = i2 % WG_STAGES;
+                    if (i2 >= WG_STAGES) c_mbar_wait(&empty[s], ((i2 / WG_STAGES) - 1) & 1);
+                    c_unpool_emit(stages + (size_t)s * WG_STAGE_B, in1, scale, g, row0, 16, gated);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) colacc[k] += gated[k];
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    c_mbar_arrive(&full[s]);
+                }
+                it.next(); it.next(); it.next(); it.next();
+            }
+            // lanes l, l+8, l+16, l+24 serve the same channel group: reduce them, one plain store per warp
+            // (shared-memory float atomics are CAS loops: 512 threads on 64 addresses cost microseconds)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                colacc[k] += __shfl_xor_sync(0xffffffffu, colacc[k], 8);
+                colacc[k] += __shfl_xor_sync(0xffffffffu, colacc[k], 16);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s_db[warp * COUT + g * 8 + k] = colacc[k];
+            }
+        }
         // M = 64 accumulator: row o lives in TMEM lane (o % 16) + 32 * (o / 16): lanes 0..15 of each quadrant.
         // warp = (quadrant, tap group): 16 lanes write the 128-byte (o, tap) rows of the fp32 partial tile.
         const int quad = warp & 3, tg = warp >> 2;                       // taps tg, tg+4, tg+8
-        float* mine = partials + (size_t)blockIdx.x * WG_OUT + (size_t)(quad * 16 + (lane & 15)) * (TAPS * CIN);
+        float* mine = partials + (size_t)blockIdx.x * WG_PART + (size_t)(quad * 16 + (lane & 15)) * (TAPS * CIN);
 #pragma unroll 1
         for (int t = tg; t < TAPS; t += 4) {
             c_mbar_wait(&tap_full[t], 0);
@@ -603,6 +747,15 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
                            make_float4(__uint_as_float(acc[j >> 4][j & 15]), __uint_as_float(acc[j >> 4][(j & 15) + 1]),
                                        __uint_as_float(acc[j >> 4][(j & 15) + 2]),
                                        __uint_as_float(acc[j >> 4][(j & 15) + 3])));
+            }
+        }
+        if (UNPOOL) {
+            asm volatile("bar.sync 1, %0;" ::"r"(WG_WORK_WARPS * 32) : "memory");     // all producers added their db
+            if (threadIdx.x < COUT) {
+                float a = 0.f;
+#pragma unroll
+                for (int q = 0; q < WG_WORK_WARPS; ++q) a += s_db[q * COUT + threadIdx.x];
+                __stcg(partials + (size_t)blockIdx.x * WG_PART + WG_OUT + threadIdx.x, a);
             }
         }
         __threadfence();
@@ -640,7 +793,7 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
     __syncthreads();
     if (threadIdx.x == 0) C_MARK(8);
     // slice of the outputs owned by this CTA (float4 units), summed over the partials in a fixed order
-    constexpr int TOTAL4 = WG_OUT / 4;
+    constexpr int TOTAL4 = (UNPOOL ? WG_PART : WG_OUT) / 4, STRIDE4 = WG_PART / 4;
     const int per = (TOTAL4 + (int)gridDim.x - 1) / (int)gridDim.x;
     const int lo = (int)blockIdx.x * per, hi = min(lo + per, TOTAL4);
     const int len = max(hi - lo, 0);
@@ -651,7 +804,9 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
         uint2 packed;
         packed.x = *reinterpret_cast<uint32_t*>(&l2);
         packed.y = *reinterpret_cast<uint32_t*>(&h2);
-        *reinterpret_cast<uint2*>(dw + (size_t)(lo + f) * 4) = packed;
+        const int e = (lo + f) * 4;                                  // outputs [0, WG_OUT) = dW, then db
+        if (e < WG_OUT) *reinterpret_cast<uint2*>(dw + e) = packed;
+        else *reinterpret_cast<uint2*>(db + (e - WG_OUT)) = packed;
     };
     if (len > 0 && 2 * len <= WG_THREADS) {
         // few outputs per CTA (the usual case: 32): `parts` thread groups split the list of partials
@@ -662,7 +817,7 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
         if (part < parts) {
 #pragma unroll 8
             for (int q = part; q < n_part; q += parts) {
-                const float4 v = __ldcg(src + (size_t)q * TOTAL4 + f);
+                const float4 v = __ldcg(src + (size_t)q * STRIDE4 + f);
                 s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
             }
         }
@@ -680,7 +835,7 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
             float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
             for (int q = 0; q < n_part; ++q) {
-                const float4 v = __ldcg(src + (size_t)q * TOTAL4 + f);
+                const float4 v = __ldcg(src + (size_t)q * STRIDE4 + f);
                 s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
             }
             store(f, s4);
@@ -883,9 +1038,13 @@ bool c_init() {
     if (!c_attr_set) {
         if (cudaFuncSetAttribute(tfy_conv3x3_fprop_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)FP_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(tfy_conv3x3_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute(tfy_conv3x3_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)DG_SMEM) != cudaSuccess ||
-            cudaFuncSetAttribute(tfy_conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute(tfy_conv3x3_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)DG_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(tfy_conv3x3_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)WG_SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(tfy_conv3x3_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)WG_SMEM) != cudaSuccess)
             return false;
         int dev = 0;
@@ -932,7 +1091,7 @@ int tfy_conv_set_timeline(long long* buf) {
 }
 
 // number of fp32 elements of the `partials` scratch buffer tfy_conv3x3_c32_wgrad needs
-size_t tfy_conv3x3_c32_wgrad_scratch_elems() { return (size_t)160 * WG_OUT; }
+size_t tfy_conv3x3_c32_wgrad_scratch_elems() { return (size_t)160 * WG_PART; }
 
 // a: [B, H, W, 32] bf16 (NHWC), w: [64, 3, 3, 32] bf16, bias: [64] bf16
 // pooled / code: [B, (H-2)/2, (W-2)/2, 64].  Requires (H-2) % 8 == 0, (W-2) % 8 == 0, B % 2 == 0.
@@ -959,8 +1118,8 @@ int tfy_conv3x3_c32_dgrad(const void* dz, const void* w, const void* gate, void*
     CUtensorMap mz, mw;
     if (!c_map_nhwc(&mz, dz, B, H - 2, W - 2, COUT, HALO, HALO) || !c_map_w(&mw, w)) return -6;
     const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8, n_patches = tiles_x * tiles_y * (B / 2);
-    tfy_launch_pdl((tfy_conv3x3_dgrad_kernel), dim3(c_grid(n_patches)), dim3(DG_THREADS), DG_SMEM, s, 
-        mz, mw, (const __nv_bfloat16*)gate, (__nv_bfloat16*)dx, H, W, tiles_x, tiles_y, n_patches);
+    tfy_launch_pdl((tfy_conv3x3_dgrad_kernel<false>), dim3(c_grid(n_patches)), dim3(DG_THREADS), DG_SMEM, s, 
+        mz, mw, (const __nv_bfloat16*)gate, (__nv_bfloat16*)dx, H, W, tiles_x, tiles_y, n_patches, (const __nv_bfloat16*)nullptr, (const uint8_t*)nullptr, 1.0f);
     return (int)cudaGetLastError();
 }
 
@@ -974,8 +1133,39 @@ int tfy_conv3x3_c32_wgrad(const void* a, const void* dz, float* partials, void* 
     CUtensorMap mz, ma;
     if (!c_map_nhwc(&mz, dz, B, OH, OW, COUT, 8, 8) || !c_map_nhwc(&ma, a, B, H, W, CIN, HALO, HALO)) return -6;
     const int tiles_x = OW / 8, tiles_y = OH / 8, n_patches = tiles_x * tiles_y * (B / 2);
-    tfy_launch_pdl((tfy_conv3x3_wgrad_kernel), dim3(c_grid(n_patches)), dim3(WG_THREADS), WG_SMEM, s, mz, ma, partials, (__nv_bfloat16*)dw, sync,
-                                                                            tiles_x, tiles_y, n_patches);
+    tfy_launch_pdl((tfy_conv3x3_wgrad_kernel<false>), dim3(c_grid(n_patches)), dim3(WG_THREADS), WG_SMEM, s, mz, ma,
+                   partials, (__nv_bfloat16*)dw, sync, tiles_x, tiles_y, n_patches, (const __nv_bfloat16*)nullptr,
+                   (const uint8_t*)nullptr, 1.0f, (__nv_bfloat16*)nullptr, 0, 0);
+    return (int)cudaGetLastError();
+}
+
+// Fused pool/dropout/ReLU backward variants: instead of a materialised dz they take the pooled gradient
+// dp [B, (H-2)/2, (W-2)/2, 64] bf16, the forward kernel's code bytes (same shape) and the dropout scale.
+int tfy_conv3x3_c32_dgrad_unpool(const void* dp, const void* code, float scale, const void* w, const void* gate,
+                                 void* dx, int B, int H, int W, cudaStream_t s) {
+    if ((B % 2) || ((H - 2) % 8) || ((W - 2) % 8)) return -2;
+    if (!c_init()) return -4;
+    CUtensorMap mw;
+    if (!c_map_w(&mw, w)) return -6;
+    const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8, n_patches = tiles_x * tiles_y * (B / 2);
+    tfy_launch_pdl((tfy_conv3x3_dgrad_kernel<true>), dim3(c_grid(n_patches)), dim3(DG_THREADS), DG_SMEM, s, mw, mw,
+                   (const __nv_bfloat16*)gate, (__nv_bfloat16*)dx, H, W, tiles_x, tiles_y, n_patches,
+                   (const __nv_bfloat16*)dp, (const uint8_t*)code, scale);
+    return (int)cudaGetLastError();
+}
+
+// also writes db [64] = sum over batch and positions of the gated pooled gradient
+int tfy_conv3x3_c32_wgrad_unpool(const void* a, const void* dp, const void* code, float scale, float* partials,
+                                 void* dw, void* db, uint32_t* sync, int B, int H, int W, cudaStream_t s) {
+    const int OH = H - 2, OW = W - 2;
+    if ((OH % 8) || (OW % 8) || (B % 2)) return -2;
+    if (!c_init() || c_sms > 160) return -4;
+    CUtensorMap ma;
+    if (!c_map_nhwc(&ma, a, B, H, W, CIN, HALO, HALO)) return -6;
+    const int tiles_x = OW / 8, tiles_y = OH / 8, n_patches = tiles_x * tiles_y * (B / 2);
+    tfy_launch_pdl((tfy_conv3x3_wgrad_kernel<true>), dim3(c_grid(n_patches)), dim3(WG_THREADS), WG_SMEM, s, ma, ma,
+                   partials, (__nv_bfloat16*)dw, sync, tiles_x, tiles_y, n_patches, (const __nv_bfloat16*)dp,
+                   (const uint8_t*)code, scale, (__nv_bfloat16*)db, OH / 2, OW / 2);
     return (int)cudaGetLastError();
 }
 
