@@ -30,7 +30,7 @@ counter = torch.zeros(1, dtype=torch.int32, device=dev)
 
 def run():
     return lib.tfy_dense_head_fused(h.data_ptr(), w2.data_ptr(), b2.data_ptr(), y.data_ptr(), mask.data_ptr(),
-                                    ctypes.c_float(2.0), loss.data_ptr(), stats.data_ptr(), dw2.data_ptr(),
+                                    ctypes.c_float(2.0), loss.data_ptr(), None, stats.data_ptr(), dw2.data_ptr(),
                                     db2.data_ptr(), dh.data_ptr(), db1.data_ptr(), scratch.data_ptr(),
                                     counter.data_ptr(), B, K, C, torch.cuda.current_stream().cuda_stream)
 

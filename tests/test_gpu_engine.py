@@ -309,7 +309,7 @@ def test_fused_dense_head_matches_autograd(B, K, C):
     ref_dh = hf.grad * mask.float() * scale
     for _ in range(2):      # twice: the scratch buffer and the counter must come back clean
         rc = lib.tfy_dense_head_fused(h.data_ptr(), w2.data_ptr(), b2.data_ptr(), y.data_ptr(), mask.data_ptr(),
-                                      ctypes.c_float(scale), loss.data_ptr(), stats.data_ptr(), dw2.data_ptr(),
+                                      ctypes.c_float(scale), loss.data_ptr(), None, stats.data_ptr(), dw2.data_ptr(),
                                       db2.data_ptr(), dh.data_ptr(), db1.data_ptr(), scratch.data_ptr(),
                                       counter.data_ptr(), B, K, C, torch.cuda.current_stream().cuda_stream)
         assert rc == 0

@@ -20,6 +20,8 @@ all-reduce of the gradients, ``torch.optim`` with the same update formulas.
 """
 from __future__ import annotations
 
+import ctypes
+
 import logging
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -206,6 +208,15 @@ class GraphTrainEngine:
         # (i+1) % 2 while graph[i % 2] runs, and no staging -> static copy sits in front of every step
         self._staging = [(_clone_struct(x), _clone_struct(y)) for _ in range(2)]
         self._static_x, self._static_y = self._staging[0]
+        self._loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._loss_in_host = [False, False]
+        self._capture_slot = None
+        self._ready_ev = [torch.cuda.Event() for _ in range(2)]
+        self._done_ev = [torch.cuda.Event() for _ in range(2)]
+        from tf_yarn_b200.ops import native
+        native.declare("tfy_memcpy_async", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])
+        self._lib = native.load()
+        self._fast_copy = hasattr(self._lib, "tfy_memcpy_async")
         fused = self.fused
         snap = (fused.master.clone(), fused.s1.clone(), fused.s2.clone(), fused.flat_params.clone(),
                 fused.hyper.clone(), self._metric_acc.clone())
@@ -228,8 +239,12 @@ class GraphTrainEngine:
                     sx, sy = self._staging[slot]
                     # the graphs never run concurrently (same stream), so they share one memory pool
                     pool = self.graphs[0].pool() if slot else None
+                    self._capture_slot = slot
                     with torch.cuda.graph(g, stream=self.stream, pool=pool):
                         self._forward_backward(sx, sy)
+                        if not self._loss_in_host[slot]:      # (the fast path's head kernel writes it itself)
+                            self._loss_host[slot].copy_(self._loss, non_blocking=True)     # D2H node of the graph
+                    self._capture_slot = None
                     self.graphs[slot] = g
                 self.graph = self.graphs[0]
             finally:
@@ -261,30 +276,54 @@ class GraphTrainEngine:
         slot = self._slot
         self._slot ^= 1
         sx, sy = self._staging[slot]
-        if self._slot_free[slot] is not None:
-            self.copy_stream.wait_event(self._slot_free[slot])
-        with torch.cuda.stream(self.copy_stream):
-            _copy_struct(sx, x)
-            _copy_struct(sy, y)
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
+        cs = self.copy_stream
+        free = self._slot_free[slot]
+        if free is not None:
+            cs.wait_event(free)
+        if (self._fast_copy and torch.is_tensor(x) and torch.is_tensor(y) and x.dtype == sx.dtype
+                and y.dtype == sy.dtype and x.is_contiguous() and y.is_contiguous()
+                and x.numel() == sx.numel() and y.numel() == sy.numel()):
+            # hot path: two cudaMemcpyAsync calls through ctypes, no stream context manager
+            lib, sp = self._lib, cs.cuda_stream
+            lib.tfy_memcpy_async(sx.data_ptr(), x.data_ptr(), x.numel() * x.element_size(), sp)
+            lib.tfy_memcpy_async(sy.data_ptr(), y.data_ptr(), y.numel() * y.element_size(), sp)
+        else:
+            with torch.cuda.stream(cs):
+                _copy_struct(sx, x)
+                _copy_struct(sy, y)
+        ev = self._ready_ev[slot]
+        ev.record(cs)
         return slot, ev
 
     def launch_step(self, ticket) -> torch.cuda.Event:
-        """Run one captured step on the staged batch; returns the event marking its completion."""
+        """Run one captured step on the staged batch; returns the event marking its completion.
+
+        The step's loss is copied to ``loss_host(slot)`` (pinned) by the graph itself."""
         slot, ready = ticket
-        sx, sy = self._staging[slot]
-        self.stream.wait_event(ready)
-        with torch.cuda.stream(self.stream):
-            if self.graph is not None:
-                self.graphs[slot].replay()
-            else:
-                self._forward_backward(sx, sy)
-            done = torch.cuda.Event()
-            done.record(self.stream)
-            self._slot_free[slot] = done          # the slot may be refilled once this step has run
+        st = self.stream
+        st.wait_event(ready)
+        if torch.cuda.current_stream() == st:
+            self._launch_on_current(slot)
+        else:
+            with torch.cuda.stream(st):
+                self._launch_on_current(slot)
+        done = self._done_ev[slot]
+        done.record(st)
+        self._slot_free[slot] = done          # the slot may be refilled once this step has run
         self.kernel_launches += self._launches_per_step
         return done
+
+    def _launch_on_current(self, slot: int) -> None:
+        if self.graph is not None:
+            self.graphs[slot].replay()
+        else:
+            sx, sy = self._staging[slot]
+            self._forward_backward(sx, sy)
+            self._loss_host[slot].copy_(self._loss, non_blocking=True)
+
+    def loss_host(self, slot: int) -> torch.Tensor:
+        """Pinned scalar that receives the loss of the steps run on ``slot`` (valid once their event fired)."""
+        return self._loss_host[slot]
 
     def read_loss_async(self, pinned_slot: torch.Tensor) -> None:
         with torch.cuda.stream(self.stream):

@@ -44,8 +44,8 @@ native.declare("tfy_conv3x3_c1_wgrad_tc", [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i,
 native.declare("tfy_conv3x3_c32_dgrad_unpool", [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad_unpool", [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_dense_head_scratch_elems", [_i, _i], restype=ctypes.c_size_t)
-native.declare("tfy_dense_head_fused", [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
-                                        _vp])
+native.declare("tfy_dense_head_fused", [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
+                                        _i, _vp])
 
 PARTIAL_BLOCKS = 592
 
@@ -195,6 +195,15 @@ class FastSequentialEngine(GraphTrainEngine):
         return (Cin == 32 and ly.filters == 64 and st.pool and st.relu and (H - 2) % 8 == 0 and (W - 2) % 8 == 0
                 and B % 2 == 0)
 
+    def _host_loss_ptr(self):
+        """Pinned scalar of the slot being captured: the head kernel stores the loss there directly (UVA), so the
+        captured step needs no D2H copy node."""
+        slot = getattr(self, "_capture_slot", None)
+        if slot is None or not getattr(self, "_loss_host", None):
+            return None
+        self._loss_in_host[slot] = True
+        return self._loss_host[slot].data_ptr()
+
     def _splitk_acc(self, key, M: int, N: int) -> torch.Tensor:
         if key not in self._acc32:
             self._acc32[key] = torch.zeros((M, N), dtype=torch.float32, device=self.device)
@@ -342,7 +351,8 @@ class FastSequentialEngine(GraphTrainEngine):
                     self._chk(lib.tfy_dense_head_fused(
                         xin.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(),
                         pmask.data_ptr() if pmask is not None else None, pscale, self._loss.data_ptr(),
-                        self._stats.data_ptr() if self.metric_fns else None, w.grad.data_ptr(), b.grad.data_ptr(),
+                        self._host_loss_ptr(), self._stats.data_ptr() if self.metric_fns else None,
+                        w.grad.data_ptr(), b.grad.data_ptr(),
                         dh.data_ptr(), pb.grad.data_ptr(), self._acc32["head_scratch"].data_ptr(),
                         self._acc32["head_counter"].data_ptr(), B, K, C, s), "dense_head_fused")
                     saved.append(("fused", dh))

@@ -336,16 +336,13 @@ class Model:
         return out
 
     def _run_epoch_pipelined(self, it, steps, cbs, first) -> Dict[str, float]:
-        """GPU loop: stage batch i+1 (H2D, copy stream) while step i runs; losses come back
-        through a pinned ring a few steps late so the host never stalls the GPU."""
+        """GPU loop: stage batch i+1 (H2D, copy stream) while step i runs.  Every captured step copies its
+        loss to a pinned scalar (a D2H node of the graph); the host reads it one step late, while the
+        next step is already queued, so it never stalls the GPU."""
         eng: GraphTrainEngine = self._engine
-        ring_n = 8
-        if not hasattr(self, "_loss_ring"):
-            self._loss_ring = torch.zeros(ring_n, dtype=torch.float32).pin_memory()
-        ring = self._loss_ring
-        events: List[Optional[torch.cuda.Event]] = [None] * ring_n
         loss_sum, n_read = 0.0, 0
         sync_every_step = cbs.needs_batch_logs
+        hooks = cbs.has_batch_hooks
 
         def fetch():
             nonlocal first
@@ -361,37 +358,35 @@ class Model:
             return {}
         ticket = eng.stage_inputs(*nxt)
         step = 0
-        while True:
-            if cbs.has_batch_hooks:
-                cbs.call("on_train_batch_begin", step, None)
-            slot = step % ring_n
-            if events[slot] is not None:       # lagged read of the loss written ring_n steps ago
-                events[slot].synchronize()
-                loss_sum += float(ring[slot])
-                n_read += 1
-            done = eng.launch_step(ticket)
-            eng.read_loss_async(ring[slot])
-            ev = torch.cuda.Event()
-            ev.record(eng.stream)
-            events[slot] = ev
-            step += 1
-            more = steps is None or step < steps
-            nxt = fetch() if more else None
-            if nxt is not None:
-                ticket = eng.stage_inputs(*nxt)
-            if cbs.has_batch_hooks:
-                logs = None
-                if sync_every_step:
-                    ev.synchronize()
-                    logs = {"loss": float(ring[slot])}
-                cbs.call("on_train_batch_end", step - 1, logs)
-            if nxt is None:
-                break
-        for slot in range(ring_n):
-            if events[slot] is not None:
-                events[slot].synchronize()
-                loss_sum += float(ring[slot])
-                n_read += 1
+        pending = None                          # (slot, event) of the step whose loss is not read yet
+        with torch.cuda.stream(eng.stream):     # one context for the epoch: replays go to the engine's stream
+            while True:
+                if hooks:
+                    cbs.call("on_train_batch_begin", step, None)
+                done = eng.launch_step(ticket)
+                slot = ticket[0]
+                step += 1
+                more = steps is None or step < steps
+                nxt = fetch() if more else None
+                if pending is not None:         # loss of the previous step: its graph finished long ago
+                    pending[1].synchronize()
+                    loss_sum += float(eng.loss_host(pending[0]))
+                    n_read += 1
+                pending = (slot, done)
+                if nxt is not None:
+                    ticket = eng.stage_inputs(*nxt)
+                if hooks:
+                    logs = None
+                    if sync_every_step:
+                        done.synchronize()
+                        logs = {"loss": float(eng.loss_host(slot))}
+                    cbs.call("on_train_batch_end", step - 1, logs)
+                if nxt is None:
+                    break
+        if pending is not None:
+            pending[1].synchronize()
+            loss_sum += float(eng.loss_host(pending[0]))
+            n_read += 1
         out = {"loss": loss_sum / max(n_read, 1)}
         out.update(eng.pop_metrics())
         return out
