@@ -185,6 +185,22 @@ def main():
     res["c1_state"] = {"ok": bool((acc1 == 0).all()) and int(cnt1.item()) == 0}
     print("c1 rc", rc, "acc zero", bool((acc1 == 0).all()), "cnt", int(cnt1.item()))
 
+    # ---------------------------------------------------------------- first-layer forward (tensor core)
+    native.declare("tfy_conv3x3_c1_fwd_tc", [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+                   + [ctypes.c_int] * 3 + [ctypes.c_void_p])
+    w1 = (torch.randn(32, 3, 3, 1, device=dev) * 0.3).to(bf16)
+    b1 = (torch.randn(32, device=dev) * 0.2).to(bf16)
+    y1 = torch.zeros(B, 26, 26, 32, dtype=bf16, device=dev)
+    y1_ref = (F.conv2d(x1b.permute(0, 3, 1, 2), w1.float().permute(0, 3, 1, 2)) + b1.float().view(1, -1, 1, 1)
+              ).relu().permute(0, 2, 3, 1)
+    for it, (xt, f32) in enumerate([(x1, 1), (x1.to(bf16), 0)]):
+        y1.zero_()
+        rc = lib.tfy_conv3x3_c1_fwd_tc(xt.data_ptr(), f32, w1.data_ptr(), b1.data_ptr(), y1.data_ptr(), B, 28, 28,
+                                       stream())
+        torch.cuda.synchronize()
+        report(f"c1_fwd_tc_{it}", y1, y1_ref, 0.01)
+    print("c1 fwd rc", rc)
+
     # ---------------------------------------------------------------- timings (hot L2; the in-graph numbers
     # come from profiles/launches_*.csv)
     t = {}
@@ -207,6 +223,10 @@ def main():
     t["pool_bwd_us"] = timeit(lambda: lib.tfy_pool_drop_relu_bwd(
         dp.data_ptr(), c2.data_ptr(), dzp.data_ptr(), ctypes.c_float(scale_u), B, 24, 24, 64, partial_u.data_ptr(),
         db_ref.data_ptr(), cnt_u.data_ptr(), stream()))
+    t["c1_fwd_tc_us"] = timeit(lambda: lib.tfy_conv3x3_c1_fwd_tc(x1.data_ptr(), 1, w1.data_ptr(), b1.data_ptr(),
+                                                                 y1.data_ptr(), B, 28, 28, stream()))
+    t["c1_fwd_cuda_core_us"] = timeit(lambda: lib.tfy_conv3x3_c1_fwd(x1.data_ptr(), 1, w1.data_ptr(), b1.data_ptr(),
+                                                                     y1.data_ptr(), B, 28, 28, 32, stream()))
     wcl = w.permute(0, 3, 1, 2)
     acl = a.permute(0, 3, 1, 2)
     dzcl = dz.permute(0, 3, 1, 2)

@@ -29,6 +29,7 @@ from tf_yarn_b200.ops import native
 
 _vp, _i, _sz, _f, _u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_uint32
 native.declare("tfy_conv3x3_c1_fwd", [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
+native.declare("tfy_conv3x3_c1_fwd_tc", [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c1_wgrad", [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp])
 native.declare("tfy_bias_act_drop_fwd", [_vp, _vp, _vp, _vp, _sz, _i, _i, _f, _u32, _vp, _vp])
 native.declare("tfy_bias_act_drop_fwd_f32", [_vp, _vp, _vp, _vp, _sz, _i, _i, _f, _u32, _vp, _vp])
@@ -259,8 +260,14 @@ class FastSequentialEngine(GraphTrainEngine):
                     # direct kernel: conv + bias + relu in one launch (relu folded only when requested)
                     a = torch.empty((B, OH, OW, O), dtype=bf16, device=cur.device)
                     if st.relu and not st.pool:
-                        self._chk(lib.tfy_conv3x3_c1_fwd(cur.data_ptr(), int(cur_is_f32), w.data_ptr(), b.data_ptr(),
-                                                         a.data_ptr(), B, H, W, O, s), "conv3x3_c1_fwd")
+                        if O == 32 and os.environ.get("TFY_NO_TC_CONV") != "1":
+                            self._chk(lib.tfy_conv3x3_c1_fwd_tc(cur.data_ptr(), int(cur_is_f32), w.data_ptr(),
+                                                                b.data_ptr(), a.data_ptr(), B, H, W, s),
+                                      "conv3x3_c1_fwd_tc")
+                        else:
+                            self._chk(lib.tfy_conv3x3_c1_fwd(cur.data_ptr(), int(cur_is_f32), w.data_ptr(),
+                                                             b.data_ptr(), a.data_ptr(), B, H, W, O, s),
+                                      "conv3x3_c1_fwd")
                         fused_pre = True
                         z = a
                     else:

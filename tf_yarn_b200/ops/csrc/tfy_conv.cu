@@ -1019,6 +1019,152 @@ tfy_conv3x3_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const
     if (threadIdx.x == 0) C_MARK(10);
 }
 
+// ------------------------------------------------------------------------------------------------
+// First-layer forward (C_in = 1, 32 filters) on the tensor core:
+//   y[pix, o] = relu( sum_k X~[pix, k] W~[o, k] ),  X~[pix, 0..8] = x[pix + tap], X~[pix, 9] = 1,  W~[o, 9] = bias[o]
+// One M128 N32 K16 tcgen05.mma per 128 pixels; both operands are built in shared memory in the un-swizzled
+// K-major core-matrix layout ([k half][row][16 B]: lbo = distance between the halves, sbo = 128).  The CUDA-core
+// version spent its time on 288 shared-memory weight loads + FMAs per pixel; here a thread gathers 9 inputs,
+// stores 2 x 16 B, and later packs 32 accumulator columns.
+// warps 0..3 build X~, warps 4..7 epilogue (TMEM quadrant = warp & 3), warp 8 MMA.
+// ------------------------------------------------------------------------------------------------
+constexpr int F1_STAGES = 4, F1_PIX = 128, F1_A_B = 2 * F1_PIX * 16;      // 4 KB per stage
+constexpr int F1_W_B = 2 * C1_O * 16;                                     // 1 KB
+constexpr int F1_THREADS = 9 * 32;
+constexpr size_t F1_SMEM = (size_t)F1_STAGES * F1_A_B + F1_W_B + 128 + 256;
+
+__device__ __forceinline__ uint64_t c_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(F1_THREADS, 2)
+tfy_conv3x3_c1_fwd_tc_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                             const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ y, int H, int W,
+                             int n_pix, int n_chunks) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* w_tile = stages + (size_t)F1_STAGES * F1_A_B;          // [2 k halves][32 o][16 B]
+    uint64_t* full = reinterpret_cast<uint64_t*>(w_tile + F1_W_B);
+    uint64_t* empty = full + F1_STAGES;
+    uint64_t* tfull = empty + F1_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F1_STAGES; ++s) { c_mbar_init(&full[s], 128); c_mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { c_mbar_init(&tfull[b], 1); c_mbar_init(&tempty[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) c_tmem_alloc<64>(tmem_slot);
+    tfy_pdl_sync();                      // (the weights below are produced by the previous step's optimizer kernel)
+    if (threadIdx.x < C1_O) {
+        // W~ row o: taps 0..7 | tap 8, bias, 0 x 6
+        const int o = threadIdx.x;
+        float k0[8], k1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < 8; ++t) k0[t] = __bfloat162float(w[o * 9 + t]);
+        k1[0] = __bfloat162float(w[o * 9 + 8]);
+        k1[1] = __bfloat162float(bias[o]);
+        *reinterpret_cast<uint4*>(w_tile + o * 16) = TfyPack<__nv_bfloat16>::pack(k0);
+        *reinterpret_cast<uint4*>(w_tile + C1_O * 16 + o * 16) = TfyPack<__nv_bfloat16>::pack(k1);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    c_fence_before();
+    __syncthreads();
+    c_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_chunks = ((int)blockIdx.x < n_chunks) ? (n_chunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int OH = H - 2, OW = W - 2;
+
+    if (warp == 8) {
+        if (c_elect_one()) {
+            const uint32_t idesc = c_idesc(128, C1_O, 0, 0);
+            const uint64_t bdesc = c_desc_nosw(c_smem_u32(w_tile), C1_O * 16, 128);
+            for (int i = 0; i < my_chunks; ++i) {
+                const int s = i % F1_STAGES, b = i & 1;
+                c_mbar_wait(&full[s], (i / F1_STAGES) & 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (i >= 2) c_mbar_wait(&tempty[b], ((i >> 1) - 1) & 1);
+                c_fence_after();
+                const uint64_t adesc = c_desc_nosw(c_smem_u32(stages + (size_t)s * F1_A_B), F1_PIX * 16, 128);
+                c_umma(tmem_base + (uint32_t)(b * C1_O), adesc, bdesc, idesc, 0u);
+                c_commit(&empty[s]);
+                c_commit(&tfull[b]);
+            }
+        }
+    } else if (warp < 4) {
+        // ---------------- im2col builders: one pixel per thread per chunk; the next chunk's inputs are loaded
+        // before this chunk's stage is waited for
+        const int r = threadIdx.x;
+        auto gather = [&](int chunk, float* v) -> bool {
+            const int p = chunk * F1_PIX + r;
+            const bool ok = p < n_pix;
+            if (ok) {
+                const int b = p / (OH * OW), rem = p - b * (OH * OW), yy = rem / OW, xx = rem - yy * OW;
+                const XT* src = x + ((size_t)b * H + yy) * W + xx;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) v[kh * 3 + kw] = (float)src[kh * W + kw];
+            } else {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) v[t] = 0.f;
+            }
+            return ok;
+        };
+        float v[9];
+        bool ok = my_chunks > 0 ? gather((int)blockIdx.x, v) : false;
+        for (int i = 0; i < my_chunks; ++i) {
+            const int s = i % F1_STAGES;
+            float c1[8] = {v[8], ok ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const uint4 q0 = TfyPack<__nv_bfloat16>::pack(v), q1 = TfyPack<__nv_bfloat16>::pack(c1);
+            if (i + 1 < my_chunks) ok = gather((int)blockIdx.x + (i + 1) * (int)gridDim.x, v);
+            if (i >= F1_STAGES) c_mbar_wait(&empty[s], ((i / F1_STAGES) - 1) & 1);
+            uint8_t* st = stages + (size_t)s * F1_A_B;
+            *reinterpret_cast<uint4*>(st + r * 16) = q0;
+            *reinterpret_cast<uint4*>(st + F1_PIX * 16 + r * 16) = q1;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            c_mbar_arrive(&full[s]);
+        }
+    } else {
+        // ---------------- epilogue: accumulator row = pixel of the chunk; ReLU, bf16, 64 contiguous bytes
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;
+        for (int i = 0; i < my_chunks; ++i) {
+            const int b = i & 1;
+            const int chunk = (int)blockIdx.x + i * (int)gridDim.x;
+            c_mbar_wait(&tfull[b], (i >> 1) & 1);
+            c_fence_after();
+            uint32_t acc[2][16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * C1_O);
+            c_tmem_ld16(taddr, acc[0]);
+            c_tmem_ld16(taddr + 16, acc[1]);
+            c_tmem_ld_wait();
+            c_fence_before();
+            c_mbar_arrive(&tempty[b]);
+            const int p = chunk * F1_PIX + r;
+            if (p < n_pix) {
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[j] = fmaxf(__uint_as_float(acc[j >> 4][j & 15]), 0.f);
+                __nv_bfloat16* yp = y + (size_t)p * C1_O;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) tfy_st16(yp + j, TfyPack<__nv_bfloat16>::pack(o + j));
+            }
+        }
+    }
+    c_fence_before();
+    __syncthreads();
+    if (warp == 8) c_tmem_free<64>(tmem_base);
+}
+
 namespace {
 using CEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1166,6 +1312,25 @@ int tfy_conv3x3_c32_wgrad_unpool(const void* a, const void* dp, const void* code
     tfy_launch_pdl((tfy_conv3x3_wgrad_kernel<true>), dim3(c_grid(n_patches)), dim3(WG_THREADS), WG_SMEM, s, ma, ma,
                    partials, (__nv_bfloat16*)dw, sync, tiles_x, tiles_y, n_patches, (const __nv_bfloat16*)dp,
                    (const uint8_t*)code, scale, (__nv_bfloat16*)db, OH / 2, OW / 2);
+    return (int)cudaGetLastError();
+}
+
+// First-layer (C_in = 1, 32 filters) forward with bias + ReLU.  x: [B, H, W, 1] fp32 or bf16, w: [32, 3, 3, 1] bf16,
+// bias: [32] bf16, y: [B, H-2, W-2, 32] bf16.
+int tfy_conv3x3_c1_fwd_tc(const void* x, int x_is_f32, const void* w, const void* bias, void* y, int B, int H, int W,
+                          cudaStream_t s) {
+    if (!c_init()) return -4;
+    const long long n_pix_ll = (long long)B * (H - 2) * (W - 2);
+    if (n_pix_ll >= (1ll << 31) - F1_PIX) return -3;
+    const int n_pix = (int)n_pix_ll, n_chunks = (n_pix + F1_PIX - 1) / F1_PIX;
+    const int grid = n_chunks < 2 * c_sms ? n_chunks : 2 * c_sms;
+    if (x_is_f32)
+        tfy_launch_pdl((tfy_conv3x3_c1_fwd_tc_kernel<float>), dim3(grid), dim3(F1_THREADS), F1_SMEM, s, (const float*)x,
+                       (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y, H, W, n_pix, n_chunks);
+    else
+        tfy_launch_pdl((tfy_conv3x3_c1_fwd_tc_kernel<__nv_bfloat16>), dim3(grid), dim3(F1_THREADS), F1_SMEM, s,
+                       (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (const __nv_bfloat16*)bias, (__nv_bfloat16*)y,
+                       H, W, n_pix, n_chunks);
     return (int)cudaGetLastError();
 }
 
