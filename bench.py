@@ -150,6 +150,9 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL print its version banner on stdout, in front of the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     from tf_yarn_b200 import hvd, keras
     from tf_yarn_b200.models.mnist_cnn import keras_mnist_cnn

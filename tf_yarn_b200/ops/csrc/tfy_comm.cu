@@ -200,34 +200,43 @@ tfy_fused_step_kernel(TfyCommCtx c, uint64_t grad_off, uint64_t param_off, size_
     }
     const bool first_step = (step == 0);
 
-    if (MODE != TFY_MODE_LOCAL) tfy_block_barrier(c);  // all ranks finished backward
-
     const size_t groups = shard_n / 8;
     const size_t shard_start = (MODE == TFY_MODE_LOCAL) ? 0 : shard_n * (size_t)c.rank;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    constexpr bool TWO = (OPT == TFY_OPT_ADADELTA || OPT == TFY_OPT_ADAM);
+
+    // The owned master / optimizer-state shard does not depend on the peers: its loads are issued BEFORE the
+    // cross-GPU barrier and before the (2-3 us) in-switch reduction, so their latency hides behind both.
+    float4 m0, m1, x0, x1, y0, y1;
+    auto load_state = [&](size_t g8) {
+        const float4* mp = reinterpret_cast<const float4*>(master + g8 * 8);
+        m0 = mp[0]; m1 = mp[1];
+        const float4* sp = reinterpret_cast<const float4*>(s1 + g8 * 8);
+        x0 = sp[0]; x1 = sp[1];
+        if (TWO) {
+            const float4* tp = reinterpret_cast<const float4*>(s2 + g8 * 8);
+            y0 = tp[0]; y1 = tp[1];
+        }
+    };
+    if (tid < groups) load_state(tid);
+
+    if (MODE != TFY_MODE_LOCAL) tfy_block_barrier(c);  // all ranks finished backward
 
     for (size_t g8 = tid; g8 < groups; g8 += nthreads) {
         const size_t e = shard_start + g8 * 8;
+        if (g8 != tid) load_state(g8);
         float g[8];
 #pragma unroll
         for (int k = 0; k < NG; ++k)
             tfy_reduce_pack<GT, MODE>(c, grad_off + e * sizeof(GT) + k * 16, g + k * GP::N);
         float4* mp = reinterpret_cast<float4*>(master + g8 * 8);
-        float4 m0 = mp[0], m1 = mp[1];
         float p[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-        float a[8], b[8];
-        {
-            float4* sp = reinterpret_cast<float4*>(s1 + g8 * 8);
-            float4 x0 = sp[0], x1 = sp[1];
-            a[0] = x0.x; a[1] = x0.y; a[2] = x0.z; a[3] = x0.w;
-            a[4] = x1.x; a[5] = x1.y; a[6] = x1.z; a[7] = x1.w;
-        }
-        if (OPT == TFY_OPT_ADADELTA || OPT == TFY_OPT_ADAM) {
-            float4* sp = reinterpret_cast<float4*>(s2 + g8 * 8);
-            float4 x0 = sp[0], x1 = sp[1];
-            b[0] = x0.x; b[1] = x0.y; b[2] = x0.z; b[3] = x0.w;
-            b[4] = x1.x; b[5] = x1.y; b[6] = x1.z; b[7] = x1.w;
+        float a[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        float b[8];
+        if (TWO) {
+            b[0] = y0.x; b[1] = y0.y; b[2] = y0.z; b[3] = y0.w;
+            b[4] = y1.x; b[5] = y1.y; b[6] = y1.z; b[7] = y1.w;
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) b[k] = 0.f;
