@@ -184,7 +184,8 @@ class FastSequentialEngine(GraphTrainEngine):
         k_tiles = (K + 63) // 64
         if K % 8 or tiles > 8 or k_tiles < 32:
             return 1
-        return max(1, min(k_tiles // 6, 24 // tiles))      # 6 k-tiles per CTA == the TMA ring depth
+        per_cta = int(os.environ.get("TFY_SPLITK_TILES", "6"))   # k-tiles per CTA (6 == the TMA ring depth)
+        return max(1, min(k_tiles // per_cta, 144 // tiles))
 
     @staticmethod
     def _tc_conv(st, B: int) -> bool:

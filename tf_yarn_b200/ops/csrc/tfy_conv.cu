@@ -940,14 +940,12 @@ tfy_conv3x3_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const
             C_MARK(5);
         }
     } else {
-        // ---------------- im2col builders: one pixel per thread per chunk
+        // ---------------- im2col builders: one pixel per thread per chunk; the next chunk's inputs are gathered
+        // before this chunk is packed and stored (one exposed L2 round trip instead of one per chunk)
         const int r = threadIdx.x;                                  // row of the stage, 0..127
         const uint32_t sw = (uint32_t)(r & 7);
-        for (int i = 0; i < my_chunks; ++i) {
-            const int s = i % C1_STAGES;
-            const int chunk = (int)blockIdx.x + i * (int)gridDim.x;
+        auto gather = [&](int chunk, float* v) -> bool {
             const int p = chunk * C1_PIX + r;
-            float v[9];
             const bool ok = p < n_pix;
             if (ok) {
                 const int b = p / (OH * OW), rem = p - b * (OH * OW), y = rem / OW, xx = rem - y * OW;
@@ -960,8 +958,15 @@ tfy_conv3x3_c1_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dz, const
 #pragma unroll
                 for (int t = 0; t < 9; ++t) v[t] = 0.f;
             }
+            return ok;
+        };
+        float v[9];
+        bool ok = my_chunks > 0 ? gather((int)blockIdx.x, v) : false;
+        for (int i = 0; i < my_chunks; ++i) {
+            const int s = i % C1_STAGES;
             float c1[8] = {v[8], ok ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const uint4 q0 = TfyPack<__nv_bfloat16>::pack(v), q1 = TfyPack<__nv_bfloat16>::pack(c1);
+            if (i + 1 < my_chunks) ok = gather((int)blockIdx.x + (i + 1) * (int)gridDim.x, v);
             if (i >= C1_STAGES) c_mbar_wait(&empty[s], ((i / C1_STAGES) - 1) & 1);
             uint8_t* rowp = stages + (size_t)s * C1_STAGE_B + (size_t)r * 128;
             *reinterpret_cast<uint4*>(rowp + ((0u ^ sw) << 4)) = q0;    // 128B swizzle: chunk ^= row & 7
