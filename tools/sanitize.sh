@@ -10,3 +10,7 @@ for TOOL in memcheck racecheck; do
     python -m pytest tests/test_gpu_engine.py -m gpu -q -k "nn_kernels or fused_step_local or tcgen05" || true
   tail -5 "$OUT/sanitizer_$TOOL.log"
 done
+# tcgen05 / TMA conv kernels, first-layer tensor-core kernels, fused un-pool producers and the fused head
+timeout 300 compute-sanitizer --tool memcheck --log-file "$OUT/sanitizer_memcheck_conv.log" \
+  python tests/gpu/conv_check.py 2 || true
+tail -3 "$OUT/sanitizer_memcheck_conv.log"
