@@ -71,3 +71,23 @@ def test_state_dict_is_the_inner_modules():
     model = _model()
     ddp = DistributedDataParallel(model, _FakeComm())
     assert ddp.state_dict().keys() == model.state_dict().keys()
+
+
+def test_channels_last_parameters_get_channels_last_gradient_views():
+    """The gradient view of a channels_last conv weight must have the parameter's strides (autograd's
+    gradient layout contract) and still alias the flat bucket."""
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Conv2d(3, 8, 3), nn.ReLU(), nn.Conv2d(8, 4, 3)).to(memory_format=torch.channels_last)
+    ref = nn.Sequential(nn.Conv2d(3, 8, 3), nn.ReLU(), nn.Conv2d(8, 4, 3))
+    ref.load_state_dict(model.state_dict())
+    ddp = DistributedDataParallel(model, _FakeComm(), bucket_cap_mb=1)
+    for p in model.parameters():
+        assert p.grad.stride() == p.stride()
+    x = torch.randn(2, 3, 10, 10)
+    ddp(x).sum().backward()
+    ref(x).sum().backward()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert p.grad.stride() == p.stride()
+        assert torch.allclose(p.grad, q.grad, atol=1e-5)
+        b, i = ddp._param_bucket[id(p)]
+        assert p.grad.untyped_storage().data_ptr() == b.flat.untyped_storage().data_ptr()

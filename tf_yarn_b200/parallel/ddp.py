@@ -31,6 +31,19 @@ from tf_yarn_b200.parallel.comm import Communicator
 _FIRST_BUCKET_BYTES = 1 << 20
 
 
+def _view_like(flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
+    """View of ``flat[off:off+numel]`` with the shape AND memory layout of ``p``.
+
+    autograd's gradient layout contract wants ``grad.strides == param.strides``; a channels_last conv
+    weight therefore gets a channels_last view of its slice (otherwise every accumulation re-lays the
+    gradient out and warns)."""
+    seg = flat[off:off + p.numel()]
+    if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+        n, c, h, w = p.shape
+        return seg.view(n, h, w, c).permute(0, 3, 1, 2)
+    return seg.view_as(p)
+
+
 class _Bucket:
     __slots__ = ("params", "offsets", "flat", "pending", "launched", "event", "dtype")
 
@@ -92,7 +105,7 @@ class DistributedDataParallel(nn.Module):
             _, b.flat = self.comm.arena.empty((n,), b.dtype, align=4096)
             b.flat.zero_()
             for i, (p, o) in enumerate(zip(b.params, b.offsets)):
-                p.grad = b.flat[o:o + p.numel()].view_as(p)
+                p.grad = _view_like(b.flat, o, p)
                 self._param_bucket[id(p)] = (b, i)
             b.pending = len(b.params)
 
@@ -106,13 +119,13 @@ class DistributedDataParallel(nn.Module):
     def _grad_view(self, p: nn.Parameter) -> torch.Tensor:
         b, i = self._param_bucket[id(p)]
         o = b.offsets[i]
-        return b.flat[o:o + p.numel()].view_as(p)
+        return _view_like(b.flat, o, p)
 
     # ------------------------------------------------------------------ hooks
     def _make_hook(self, p: nn.Parameter):
         bucket, idx = self._param_bucket[id(p)]
         off = bucket.offsets[idx]
-        view = bucket.flat[off:off + p.numel()].view_as(p)
+        view = _view_like(bucket.flat, off, p)
 
         def hook(param: nn.Parameter) -> None:
             g = param.grad
@@ -179,7 +192,7 @@ class DistributedDataParallel(nn.Module):
         for b in self._buckets:
             b.flat.zero_()
             for p, o in zip(b.params, b.offsets):
-                p.grad = b.flat[o:o + p.numel()].view_as(p)
+                p.grad = _view_like(b.flat, o, p)
 
     def state_dict(self, *args, **kwargs):
         return self.module.state_dict(*args, **kwargs)
