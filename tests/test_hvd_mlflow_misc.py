@@ -118,3 +118,17 @@ def test_gen_task_cmd():
     assert _env.gen_task_cmd("py", "ps", "my.module").strip() == "py -m my.module"
     with pytest.raises(ValueError):
         _env.gen_task_cmd("py", "driver")
+
+
+def test_check_hadoop_env_entry_point_runs_the_whole_check(tmp_path, monkeypatch):
+    """Same module name as the reference's environment check: file round trip + a one-task application
+    that re-reads the file and posts `result` (reference: tf_yarn/bin/check_hadoop_env.py:125-172)."""
+    from tf_yarn_b200.bin import check_hadoop_env
+    monkeypatch.chdir(tmp_path)
+    path = check_hadoop_env.write_dummy_file(str(tmp_path))
+    assert check_hadoop_env.read_file(path) == check_hadoop_env.EXPECTED_CONTENT
+    monkeypatch.setattr(check_hadoop_env._impl, "check_native", lambda: True)   # (built by the other tests)
+    monkeypatch.setattr(check_hadoop_env._impl, "check_gpus", lambda: True)
+    assert check_hadoop_env.main([]) == 0
+    log = (tmp_path / check_hadoop_env.RESULT_CHECK_FILE).read_text()
+    assert "remote_check: True" in log and "setup: OK" in log
