@@ -14,5 +14,6 @@ setup(
     python_requires=">=3.10",
     install_requires=["torch", "cloudpickle", "numpy"],
     extras_require={"tensorboard": ["tensorboard"], "parquet": ["pyarrow"], "mlflow": ["mlflow"]},
-    entry_points={"console_scripts": ["check_b200_env = tf_yarn_b200.bin.check_env:main"]},
+    entry_points={"console_scripts": ["check_b200_env = tf_yarn_b200.bin.check_env:main",
+                                      "check_hadoop_env = tf_yarn_b200.bin.check_hadoop_env:main"]},
 )
