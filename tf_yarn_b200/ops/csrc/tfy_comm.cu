@@ -181,7 +181,11 @@ template <typename GT, typename PT, int OPT, int MODE>
 __global__ void __launch_bounds__(256)
 tfy_fused_step_kernel(TfyCommCtx c, uint64_t grad_off, uint64_t param_off, size_t shard_n,
                       float* __restrict__ master, float* __restrict__ s1, float* __restrict__ s2,
-                      TfyOptHyper* __restrict__ hp, int zero_grads) {
+                      TfyOptHyper* __restrict__ hp, int zero_grads, size_t e0, size_t e1, int advance) {
+    // [e0, e1): element range of the FLAT buffers this launch handles (multiples of 8; the whole buffer for
+    // the classic single launch).  Splitting a step into ranges lets the engine run the update of gradients
+    // that are final early (the big Dense kernel) on a side stream while backward continues; `advance` is set
+    // on the last launch of a step only, so every range of the step sees the same step counter.
     tfy_pdl_sync();
     using GP = TfyPack<GT>;
     using PP = TfyPack<PT>;
@@ -200,9 +204,13 @@ tfy_fused_step_kernel(TfyCommCtx c, uint64_t grad_off, uint64_t param_off, size_
     }
     const bool first_step = (step == 0);
 
-    const size_t groups = shard_n / 8;
     const size_t shard_start = (MODE == TFY_MODE_LOCAL) ? 0 : shard_n * (size_t)c.rank;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // part of [e0, e1) that falls into the shard this rank owns, in groups of 8 relative to the shard
+    const size_t lo_e = e0 > shard_start ? e0 - shard_start : 0;
+    const size_t hi_e = e1 > shard_start ? e1 - shard_start : 0;
+    const size_t g_lo = (lo_e < shard_n ? lo_e : shard_n) / 8;
+    const size_t groups = (hi_e < shard_n ? hi_e : shard_n) / 8;      // exclusive upper bound
+    const size_t tid = g_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     constexpr bool TWO = (OPT == TFY_OPT_ADADELTA || OPT == TFY_OPT_ADAM);
 
@@ -289,7 +297,7 @@ tfy_fused_step_kernel(TfyCommCtx c, uint64_t grad_off, uint64_t param_off, size_
         const uint32_t prev = atomicAdd(&hp->done, 1u);
         if (prev == gridDim.x - 1) {
             hp->done = 0;
-            hp->step = step + 1;
+            if (advance) hp->step = step + 1;
         }
     }
 }
@@ -365,19 +373,41 @@ int tfy_allgather(const TfyCommCtx* c, uint64_t off, size_t shard_bytes, int gri
 
 // The fused gradient step.  shard_n: elements owned by each rank (multiple of 8).
 // mode: 0 local (world==1), 1 P2P, 2 NVLS.
+int tfy_fused_step_range(const TfyCommCtx* c, int grad_dtype, int param_dtype, int opt, int mode, uint64_t grad_off,
+                         uint64_t param_off, size_t shard_n, float* master, float* s1, float* s2, TfyOptHyper* hp,
+                         int zero_grads, int grid, int block, size_t e0, size_t e1, int advance, cudaStream_t s);
+
 int tfy_fused_step(const TfyCommCtx* c, int grad_dtype, int param_dtype, int opt, int mode, uint64_t grad_off,
                    uint64_t param_off, size_t shard_n, float* master, float* s1, float* s2, TfyOptHyper* hp,
                    int zero_grads, int grid, int block, cudaStream_t s) {
-    if (shard_n % 8) return -2;
+    return tfy_fused_step_range(c, grad_dtype, param_dtype, opt, mode, grad_off, param_off, shard_n, master, s1, s2,
+                                hp, zero_grads, grid, block, 0, (size_t)-1, 1, s);
+}
+
+// element range [e0, e1) of the flat buffers (multiples of 8; e1 is clamped to the buffer), see the kernel
+int tfy_fused_step_range(const TfyCommCtx* c, int grad_dtype, int param_dtype, int opt, int mode, uint64_t grad_off,
+                         uint64_t param_off, size_t shard_n, float* master, float* s1, float* s2, TfyOptHyper* hp,
+                         int zero_grads, int grid, int block, size_t e0, size_t e1, int advance, cudaStream_t s) {
+    if (shard_n % 8 || e0 % 8 || (e1 != (size_t)-1 && e1 % 8)) return -2;
+    {
+        const size_t total = shard_n * (size_t)(mode == TFY_MODE_LOCAL ? 1 : c->world);
+        if (e1 > total) e1 = total;
+        if (e0 > e1) e0 = e1;
+    }
     if (mode == TFY_MODE_NVLS && c->mc_base == 0) return -5;
     if (block <= 0) block = (mode == TFY_MODE_LOCAL) ? 128 : 256;
     // single GPU: nothing to synchronise with, so oversubscribe the SMs for memory-level parallelism;
     // multi GPU: every CTA runs two cross-GPU barriers, keep one wave
-    if (grid <= 0) grid = tfy_pick_grid(shard_n / 8, block, mode == TFY_MODE_LOCAL ? 148 * 6 : 148 * 2);
+    if (grid <= 0) {
+        // work of the busiest rank: the largest overlap of [e0, e1) with one shard
+        size_t span = e1 - e0;
+        if (span > shard_n) span = shard_n;
+        grid = tfy_pick_grid(span / 8 + 1, block, mode == TFY_MODE_LOCAL ? 148 * 6 : 148 * 2);
+    }
     if (grid > TFY_MAX_BLOCKS) grid = TFY_MAX_BLOCKS;
 #define TFY_FS4(GT, PT, O, M)                                                                                  \
     tfy_launch_pdl((tfy_fused_step_kernel<GT, PT, O, M>), dim3(grid), dim3(block), 0, s, *c, grad_off, param_off, shard_n, master, s1, s2, \
-                                                                hp, zero_grads)
+                                                                hp, zero_grads, e0, e1, advance)
 #define TFY_FS3(GT, PT, O)                                   \
     do {                                                     \
         if (mode == TFY_MODE_LOCAL) TFY_FS4(GT, PT, O, TFY_MODE_LOCAL); \

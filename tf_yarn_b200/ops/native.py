@@ -76,6 +76,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tfy_broadcast.argtypes = [ctxp, u64, sz, i, i, i, i, vp]
     lib.tfy_allgather.argtypes = [ctxp, u64, sz, i, i, vp]
     lib.tfy_fused_step.argtypes = [ctxp, i, i, i, i, u64, u64, sz, vp, vp, vp, vp, i, i, i, vp]
+    if hasattr(lib, "tfy_fused_step_range"):
+        lib.tfy_fused_step_range.argtypes = [ctxp, i, i, i, i, u64, u64, sz, vp, vp, vp, vp, i, i, i, sz, sz, i, vp]
     for name, (args, restype) in _EXTRA_DECLS.items():
         fn = getattr(lib, name, None)
         if fn is not None:

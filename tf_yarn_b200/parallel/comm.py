@@ -10,7 +10,7 @@ tf_yarn/tensorflow/tasks/gloo_allred_task.py:54) and c10d's NCCL process group
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence
+from typing import Tuple,  List, Optional, Sequence
 
 import torch
 
@@ -366,13 +366,30 @@ class FusedShardedOptimizer:
             comm.barrier()
 
     # -- the hot path --------------------------------------------------------
-    def step(self, stream=None) -> None:
+    def step(self, stream=None, elem_range: Optional[Tuple[int, int]] = None, advance: bool = True,
+             block: int = 0) -> None:
+        """One fused update.  ``elem_range=(e0, e1)`` restricts it to that element range of the flat buffers
+        (multiples of 8): a step may be split into several launches -- e.g. the gradients that are final
+        early on a side stream while backward continues -- with ``advance=True`` on the LAST one only, so
+        that every launch of the step sees the same step counter."""
         c = self.comm
-        rc = c.lib.tfy_fused_step(
-            c.arena.ctx_ref, _DT[self.grad_dtype], _DT[self.param_dtype], self.spec.code, c.mode,
-            self.grad_off, self.param_off, self.shard_n,
-            self.master.data_ptr(), self.s1.data_ptr(), self.s2.data_ptr(), self.hyper.data_ptr(),
-            int(self.zero_grads), self.grid, self.block, _stream_ptr(stream))
+        if elem_range is None and advance:
+            rc = c.lib.tfy_fused_step(
+                c.arena.ctx_ref, _DT[self.grad_dtype], _DT[self.param_dtype], self.spec.code, c.mode,
+                self.grad_off, self.param_off, self.shard_n,
+                self.master.data_ptr(), self.s1.data_ptr(), self.s2.data_ptr(), self.hyper.data_ptr(),
+                int(self.zero_grads), self.grid, self.block, _stream_ptr(stream))
+        else:
+            if self.zero_grads:
+                raise ValueError("ranged steps do not clear gradients: construct with zero_grads=False")
+            e0, e1 = elem_range if elem_range is not None else (0, self.n)
+            if e0 % 8 or e1 % 8 or not 0 <= e0 <= e1 <= self.n:
+                raise ValueError(f"bad element range {elem_range} for a buffer of {self.n}")
+            rc = c.lib.tfy_fused_step_range(
+                c.arena.ctx_ref, _DT[self.grad_dtype], _DT[self.param_dtype], self.spec.code, c.mode,
+                self.grad_off, self.param_off, self.shard_n,
+                self.master.data_ptr(), self.s1.data_ptr(), self.s2.data_ptr(), self.hyper.data_ptr(),
+                0, 0, int(block), e0, e1, int(advance), _stream_ptr(stream))
         native.check(rc, "tfy_fused_step")
         c.launches += 1
 
