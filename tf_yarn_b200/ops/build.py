@@ -127,9 +127,30 @@ def build_kv(verbose: bool = False) -> str:
     return KV_LIB
 
 
+def build_probe(verbose: bool = False) -> str:
+    """Stand-alone tcgen05 operand-fetch probe (tests/gpu/umma_probe.cu -> tests/gpu/umma_probe), run through
+    gpurun: it measures the cycles per MMA of every operand layout and which shared-memory chunks a swizzled
+    descriptor reads.  Returns '' when the source is not there (installed package)."""
+    root = os.path.dirname(os.path.dirname(HERE))
+    src = os.path.join(root, "tests", "gpu", "umma_probe.cu")
+    out = os.path.join(root, "tests", "gpu", "umma_probe")
+    if not os.path.exists(src):
+        return ""
+    if os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O2", "-std=c++17", "-o", out, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for umma_probe.cu:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        sys.stderr.write(f"[tf_yarn_b200.build] built {out}\n")
+    return out
+
+
 def build_all(verbose: bool = True) -> None:
     build_kv(verbose)
     build_cuda(verbose)
+    build_probe(verbose)
 
 
 def sass_dump(out_dir: str) -> None:
