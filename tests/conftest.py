@@ -26,3 +26,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_libraries_built():
+    """Build the in-tree native libraries ONCE, before any test spawns worker processes: in a fresh checkout
+    every child would otherwise start its own nvcc build (and multi-process tests would time out)."""
+    from tf_yarn_b200.ops import build
+    build.build_all(verbose=False)
+    yield

@@ -23,6 +23,8 @@ def _worker(rank, world, prefix, q):
 
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_fd_exchange_all_to_all(world):
+    from tf_yarn_b200.ops import native
+    native.load()            # build once here: in a fresh checkout the children would all compile (and time out)
     ctx = mp.get_context("spawn")
     prefix = os.path.join(tempfile.gettempdir(), f"tfy_fdx_{uuid.uuid4().hex[:8]}")
     q = ctx.Queue()
