@@ -3,15 +3,22 @@
 For ``Sequential`` models made of Conv2D(3x3, valid, stride 1) / MaxPooling2D(2x2) /
 Dropout / Flatten / Dense layers with relu|linear activations and a sparse-categorical
 cross-entropy (from logits) head -- the MNIST-CNN of the headline benchmark, the wine MLP --
-the step does not go through autograd at all.  GEMM-shaped work goes to cuDNN / cuBLAS
-(library GEMMs) or to the hand-written kernels, and everything around it is fused
-(:mod:`ops/csrc/tfy_nn.cu`): bias+ReLU(+2x2 max-pool)(+dropout) in one kernel, backward
-gating + bias-gradient reduction in one kernel, the whole softmax/CE head in one kernel,
-weight gradients written straight into the flat gradient buffer consumed by the fused
-reduce-scatter/optimizer/all-gather kernel (no ``grad += g`` accumulation launches).
+the step does not go through autograd at all:
 
-22 launches per step instead of 53 (profiles/launches_*.csv).  Models outside this grammar
-use the autograd engine (:class:`GraphTrainEngine`).
+* convolutions are tcgen05 implicit GEMMs (:mod:`ops/csrc/tfy_conv.cu`): conv2 forward with
+  bias + ReLU + 2x2 max-pool + dropout in the epilogue, conv2 data / weight gradients whose dz
+  operand is rebuilt in shared memory from the pooled gradient (un-pool + dropout + ReLU gate
+  fused, db included), the first layer's forward and weight/bias gradient with im2col built in
+  shared memory;
+* the long-K Dense forward is the split-K tcgen05 GEMM (:mod:`ops/csrc/tfy_gemm.cu`);
+* the classifier head runs forward AND backward in one kernel (:mod:`ops/csrc/tfy_nn.cu`);
+* weight gradients are written straight into the flat gradient buffer consumed by the fused
+  reduce-scatter / optimizer / all-gather kernel (no ``grad += g`` accumulation launches).
+
+9 launches of our kernels + 2 cuBLAS GEMMs per MNIST-CNN step, against 53 for the autograd engine
+(profiles/launches_*.csv).  Layers or shapes outside the kernels' envelope fall back to cuDNN / cuBLAS +
+the element-wise fused kernels of ``tfy_nn.cu``; models outside the grammar use the autograd engine
+(:class:`GraphTrainEngine`).
 """
 from __future__ import annotations
 
