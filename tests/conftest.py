@@ -33,5 +33,10 @@ def _native_libraries_built():
     """Build the in-tree native libraries ONCE, before any test spawns worker processes: in a fresh checkout
     every child would otherwise start its own nvcc build (and multi-process tests would time out)."""
     from tf_yarn_b200.ops import build
-    build.build_all(verbose=False)
+    try:
+        # without nvcc (CPU-only CI runners) only the KV server is built; gpu-marked tests are skipped anyway
+        build.build_all(verbose=False, require_cuda=False)
+    except RuntimeError as exc:
+        import warnings
+        warnings.warn(f"native build incomplete: {exc}")
     yield

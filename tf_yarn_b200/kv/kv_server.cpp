@@ -18,6 +18,7 @@
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 #include <sys/socket.h>
 #include <unistd.h>
@@ -91,8 +92,36 @@ struct Server {
     uint64_t version = 0;                                       // bumps on every PUT
     std::deque<std::pair<std::string, std::string>> log;        // ordered PUT log for subscribers
     std::thread accept_thread;
+    struct Conn {
+        int fd = -1;                       // -1 once serve() has closed it
+        std::atomic<bool> done{false};     // serve() returned: the thread can be joined without blocking
+        std::thread th;
+    };
     std::mutex conn_mu;
-    std::list<std::pair<int, std::thread>> conns;
+    std::list<std::unique_ptr<Conn>> conns;
+
+    // A finished connection releases its descriptor immediately (KVClient.wait() opens one connection per call, a
+    // launcher sees hundreds of them per job); the std::thread object is joined and dropped by the next accept.
+    void finish(Conn* c) {
+        std::lock_guard<std::mutex> g(conn_mu);
+        if (c->fd >= 0) {
+            ::shutdown(c->fd, SHUT_RDWR);
+            close(c->fd);
+            c->fd = -1;
+        }
+        c->done.store(true);
+    }
+
+    void reap_locked() {
+        for (auto it = conns.begin(); it != conns.end();) {
+            if ((*it)->done.load()) {
+                if ((*it)->th.joinable()) (*it)->th.join();
+                it = conns.erase(it);
+            } else {
+                ++it;
+            }
+        }
+    }
 
     void serve(int fd) {
         int one = 1;
@@ -197,7 +226,6 @@ struct Server {
             }
             if (!ok) break;
         }
-        ::shutdown(fd, SHUT_RDWR);
     }
 
     void accept_loop() {
@@ -206,13 +234,31 @@ struct Server {
             if (fd < 0) {
                 if (stop.load()) return;
                 if (errno == EINTR) continue;
+                if (errno == EMFILE || errno == ENFILE || errno == ENOBUFS || errno == ENOMEM ||
+                    errno == ECONNABORTED || errno == EPROTO || errno == EAGAIN) {
+                    // transient: out of descriptors / aborted handshake.  Keep serving -- a store that silently
+                    // stops accepting hangs every task in kv.wait().
+                    fprintf(stderr, "[tfy_kv] accept: %s; retrying\n", strerror(errno));
+                    {
+                        std::lock_guard<std::mutex> g(conn_mu);
+                        reap_locked();
+                    }
+                    usleep(20000);
+                    continue;
+                }
+                fprintf(stderr, "[tfy_kv] accept failed permanently: %s\n", strerror(errno));
                 return;
             }
             std::lock_guard<std::mutex> g(conn_mu);
             if (stop.load()) { close(fd); return; }
-            conns.emplace_back(fd, std::thread());
-            auto& slot = conns.back();
-            slot.second = std::thread([this, fd] { serve(fd); });
+            reap_locked();
+            conns.emplace_back(new Conn());
+            Conn* c = conns.back().get();
+            c->fd = fd;
+            c->th = std::thread([this, c, fd] {
+                serve(fd);
+                finish(c);
+            });
         }
     }
 };
@@ -259,12 +305,11 @@ void tfy_kv_stop(void* h) {
     if (s->accept_thread.joinable()) s->accept_thread.join();
     {
         std::lock_guard<std::mutex> g(s->conn_mu);
-        for (auto& c : s->conns) ::shutdown(c.first, SHUT_RDWR);
+        for (auto& c : s->conns)
+            if (c->fd >= 0) ::shutdown(c->fd, SHUT_RDWR);      // wakes a thread parked in recv()
     }
-    for (auto& c : s->conns) {
-        if (c.second.joinable()) c.second.join();
-        close(c.first);
-    }
+    for (auto& c : s->conns)                                   // finish() closes the descriptors
+        if (c->th.joinable()) c->th.join();
     delete s;
 }
 

@@ -15,6 +15,8 @@ JIT cache outside the repo and no dependence on the torch C++ ABI.
 from __future__ import annotations
 
 import concurrent.futures
+import contextlib
+import fcntl
 import hashlib
 import os
 import shutil
@@ -37,6 +39,27 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
+
+
+@contextlib.contextmanager
+def _build_lock(path: str):
+    """Exclusive inter-process lock: the N rank processes a launcher starts in a fresh checkout must not compile
+    and link the same paths concurrently (one builds, the others wait and then find everything up to date)."""
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as fh:
+        fcntl.flock(fh, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(fh, fcntl.LOCK_UN)
+
+
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
 
 
 def _nvcc() -> str:
@@ -73,39 +96,47 @@ def _compile_one(src: str, verbose: bool) -> str:
     key = _digest(src, " ".join(NVCC_FLAGS))
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == key:
         return obj
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", CSRC, "-c", src, "-o", obj]
+    tmp_obj = obj + f".tmp{os.getpid()}"
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", CSRC, "-c", src, "-o", tmp_obj]
     if src.endswith(".cpp"):
         cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-x", "cu",
                "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-               "-I", CSRC, "-c", src, "-o", obj]
+               "-I", CSRC, "-c", src, "-o", tmp_obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(OBJDIR, base + ".log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
+        with contextlib.suppress(OSError):
+            os.remove(tmp_obj)
         raise RuntimeError(f"nvcc failed for {base}:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp_obj, obj)
     if verbose:
         sys.stderr.write(f"[tf_yarn_b200.build] compiled {base}\n")
-    with open(stamp, "w") as f:
+    with open(stamp + ".tmp", "w") as f:
         f.write(key)
+    os.replace(stamp + ".tmp", stamp)
     return obj
 
 
 def build_cuda(verbose: bool = False) -> str:
     """Compile every ``.cu``/``.cpp`` under ``ops/csrc`` for sm_100a and link them."""
     srcs = cuda_sources()
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile_one(s, verbose), srcs))
-    newest = max(os.path.getmtime(o) for o in objs)
-    if os.path.exists(CUDA_LIB) and os.path.getmtime(CUDA_LIB) >= newest:
+    with _build_lock(os.path.join(LIBDIR, ".build.lock")):
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+            objs = list(ex.map(lambda s: _compile_one(s, verbose), srcs))
+        newest = max(os.path.getmtime(o) for o in objs)
+        if os.path.exists(CUDA_LIB) and os.path.getmtime(CUDA_LIB) >= newest:
+            return CUDA_LIB
+        tmp = CUDA_LIB + f".tmp{os.getpid()}"
+        cmd = [_nvcc(), "-shared", "-o", tmp] + objs + ["-cudart", "static", "-lpthread", "-ldl", "-lrt"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+        os.replace(tmp, CUDA_LIB)       # a process that dlopen()s concurrently sees the old or the new file, never half
+        if verbose:
+            sys.stderr.write(f"[tf_yarn_b200.build] linked {CUDA_LIB}\n")
         return CUDA_LIB
-    cmd = [_nvcc(), "-shared", "-o", CUDA_LIB] + objs + ["-cudart", "static", "-lpthread", "-ldl", "-lrt"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        sys.stderr.write(f"[tf_yarn_b200.build] linked {CUDA_LIB}\n")
-    return CUDA_LIB
 
 
 def build_kv(verbose: bool = False) -> str:
@@ -147,8 +178,13 @@ def build_probe(verbose: bool = False) -> str:
     return out
 
 
-def build_all(verbose: bool = True) -> None:
+def build_all(verbose: bool = True, require_cuda: bool = True) -> None:
+    """Build everything.  ``require_cuda=False`` (CPU CI): without nvcc only the host-side KV server is built."""
     build_kv(verbose)
+    if not require_cuda and not have_nvcc():
+        if verbose:
+            sys.stderr.write("[tf_yarn_b200.build] nvcc not found: CUDA libraries skipped\n")
+        return
     build_cuda(verbose)
     build_probe(verbose)
 

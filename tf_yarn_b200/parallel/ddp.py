@@ -71,6 +71,7 @@ class DistributedDataParallel(nn.Module):
         self.require_backward_grad_sync = True
         self._comm_stream = torch.cuda.Stream(device=comm.device) if comm.world > 1 else None
         self._callback_queued = False
+        self._next_bucket = 0            # buckets [0, _next_bucket) have been launched in this backward
         self._buckets: List[_Bucket] = []
         self._param_bucket = {}          # id(param) -> (bucket, index in bucket); tensors compare elementwise
         self._build_buckets(int(bucket_cap_mb) << 20)
@@ -140,9 +141,20 @@ class DistributedDataParallel(nn.Module):
                 torch.autograd.Variable._execution_engine.queue_callback(self._finalize_backward)
             bucket.pending -= 1
             if bucket.pending == 0:
-                self._launch(bucket)
+                self._launch_ready_prefix()
 
         return hook
+
+    def _launch_ready_prefix(self) -> None:
+        """Launch complete buckets STRICTLY in index order (bucket i only after 0..i-1), as torch DDP does: the
+        kernels of different ranks are paired by launch order on the per-CTA flag slots, so every rank must issue
+        the same sequence even if autograd completes the buckets in a different order on some rank."""
+        while self._next_bucket < len(self._buckets):
+            b = self._buckets[self._next_bucket]
+            if b.pending != 0:
+                return
+            self._launch(b)
+            self._next_bucket += 1
 
     def _launch(self, bucket: _Bucket) -> None:
         bucket.launched = True
@@ -158,10 +170,11 @@ class DistributedDataParallel(nn.Module):
 
     def _finalize_backward(self) -> None:
         self._callback_queued = False
-        for b in self._buckets:
-            if not b.launched:
-                # parameters that received no gradient this step contribute zeros
-                self._launch(b)
+        for b in self._buckets[self._next_bucket:]:
+            # buckets still waiting for a predecessor, or whose parameters received no gradient this step
+            # (they contribute zeros -- what find_unused_parameters=True does in torch DDP), in index order
+            self._launch(b)
+        self._next_bucket = 0
         cur = torch.cuda.current_stream() if self.comm.world > 1 else None
         for b in self._buckets:
             if b.event is not None:
@@ -194,11 +207,9 @@ class DistributedDataParallel(nn.Module):
             for p, o in zip(b.params, b.offsets):
                 p.grad = _view_like(b.flat, o, p)
 
-    def state_dict(self, *args, **kwargs):
-        return self.module.state_dict(*args, **kwargs)
-
-    def load_state_dict(self, *args, **kwargs):
-        return self.module.load_state_dict(*args, **kwargs)
+    # state_dict()/load_state_dict() are nn.Module's: keys carry the ``module.`` prefix exactly like
+    # torch.nn.parallel.DistributedDataParallel, so checkpoints are interchangeable with the reference's
+    # (tf_yarn/pytorch/model_ckpt.py saves ``model.module.state_dict()`` when it sees a wrapper).
 
 
 def wrap_model(model: nn.Module, device, ddp_kwargs: Optional[dict] = None, comm: Optional[Communicator] = None):

@@ -65,8 +65,19 @@ def stop_cond_reached(stop_cond, timeout_in_secs, timestamp) -> bool:
 def _get_step(checkpoint: str) -> int:
     if "model.ckpt-" in checkpoint:
         return int(checkpoint.split("model.ckpt-")[1])
-    m = re.search(r"(\d+)(?!.*\d)", os.path.basename(checkpoint))
-    return int(m.group(1)) if m else -1
+    # Keras ModelCheckpoint names ("weights.02.h5", "model-7.pt", "ckpt_0003.keras"): the LAST integer of the
+    # stem, extension(s) stripped -- never a digit of the extension itself
+    stem = os.path.basename(checkpoint)
+    while True:
+        root, ext = os.path.splitext(stem)
+        if not ext or not root or re.fullmatch(r"\.\d+", ext):
+            break
+        stem = root
+    m = re.search(r"(\d+)(?!.*\d)", stem)
+    if m is None:
+        raise ValueError(f"cannot parse a training step out of checkpoint name {checkpoint!r}: use a "
+                         "ModelCheckpoint filepath with {epoch} or a step number in it")
+    return int(m.group(1))
 
 
 def _get_all_checkpoints(model_dir: str):
@@ -105,12 +116,23 @@ def keras_evaluate(experiment: KerasExperiment, stop_cond=None, timeout_in_secs=
     from tf_yarn_b200 import keras
     eval_dir = os.path.join(experiment.model_dir, "eval")
     evaluated = get_initial_evaluated_checkpoints(eval_dir)
+    evaluated_before = set(evaluated)
+    seen_files: Set = set()
     timestamp = datetime.now()
     writer = None
     n_done = 0
     while True:
         finished = stop_cond_reached(stop_cond, timeout_in_secs, timestamp)
-        todo = [c for c in _keras_checkpoints(experiment.model_dir) if _get_step(c) not in evaluated]
+        # dedupe on (path, mtime): two files whose names parse to the same number are both evaluated, and a
+        # checkpoint rewritten in place is evaluated again; the parsed number is only the TensorBoard step.
+        # Steps found in an existing eval directory (a restarted evaluator) are still skipped.
+        todo = []
+        for c in _keras_checkpoints(experiment.model_dir):
+            key = (c, os.path.getmtime(c))
+            if key in seen_files or _get_step(c) in evaluated_before:
+                continue
+            todo.append(c)
+            seen_files.add(key)
         for path in todo:
             timestamp = datetime.now()
             logger.info("Evaluating checkpoint %s", path)
