@@ -67,10 +67,29 @@ def test_zero_grad_set_to_none_is_recovered_and_no_sync_accumulates():
         assert torch.allclose(p.grad, 2 * g, atol=1e-5)
 
 
-def test_state_dict_is_the_inner_modules():
+def test_state_dict_keys_carry_the_module_prefix_like_torch_ddp():
+    """Checkpoints written from the wrapper are interchangeable with torch DDP's (keys `module.<name>`)."""
     model = _model()
     ddp = DistributedDataParallel(model, _FakeComm())
-    assert ddp.state_dict().keys() == model.state_dict().keys()
+    assert set(ddp.state_dict().keys()) == {"module." + k for k in model.state_dict().keys()}
+    other = DistributedDataParallel(_model(), _FakeComm())
+    other.load_state_dict(ddp.state_dict())
+    for a, b in zip(other.module.parameters(), model.parameters()):
+        assert torch.equal(a, b)
+
+
+def test_buckets_launch_strictly_in_index_order(monkeypatch):
+    """Even when autograd completes a later bucket first, kernels are issued bucket 0, 1, 2, ... (ranks pair the
+    collectives by launch order)."""
+    model = _model()
+    ddp = DistributedDataParallel(model, _FakeComm(), bucket_cap_mb=1)
+    order = []
+    monkeypatch.setattr(ddp, "_launch", lambda b: (order.append(ddp._buckets.index(b)), setattr(b, "launched", True)))
+    # complete the LAST bucket first by hand, then the others
+    for b in reversed(ddp._buckets):
+        b.pending = 0
+        ddp._launch_ready_prefix()
+    assert order == list(range(len(ddp._buckets)))
 
 
 def test_channels_last_parameters_get_channels_last_gradient_views():

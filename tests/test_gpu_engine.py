@@ -326,3 +326,61 @@ def test_fused_dense_head_matches_autograd(B, K, C):
         assert bool((scratch == 0).all()) and int(counter.item()) == 0
     assert stats[1].item() == 2 * B
     assert stats[0].item() == 2 * (logits.argmax(1) == y).sum().item()
+
+
+@pytest.mark.parametrize("B,U,I,want_dx", [(128, 128, 9216, True), (128, 128, 9216, False), (64, 128, 1000, True),
+                                            (100, 72, 200, True), (16, 8, 64, True)])
+def test_tcgen05_dense_backward_matches_fp32_reference(B, U, I, want_dx):
+    """dW = dh^T x and dx = dh W out of ONE tcgen05 kernel (MN-major operand views of the same tiles, TMA-store
+    epilogue) vs fp32 matmuls of the same bf16 inputs; ragged extents exercise the TMA zero-fill / clipping."""
+    from tf_yarn_b200.keras import fastpath  # noqa: F401  (declares the kernel)
+    from tf_yarn_b200.ops import native
+    lib = native.load()
+    g = torch.Generator(device="cuda").manual_seed(B * 3 + U * 5 + I)
+    dh = (torch.randn(B, U, device="cuda", generator=g) * 0.5).bfloat16()
+    x = (torch.randn(B, I, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(U, I, device="cuda", generator=g) * 0.5).bfloat16()
+    dw = torch.full((U, I), 7.0, dtype=torch.bfloat16, device="cuda")
+    dx = torch.full((B, I), 7.0, dtype=torch.bfloat16, device="cuda") if want_dx else None
+    rc = lib.tfy_dense_bwd(dh.data_ptr(), x.data_ptr(), w.data_ptr(), dw.data_ptr(),
+                           dx.data_ptr() if want_dx else None, B, U, I, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref_dw = dh.float().t() @ x.float()
+    assert (dw.float() - ref_dw).abs().max().item() <= 0.01 * ref_dw.abs().max().item() + 0.02, \
+        (dw.float() - ref_dw).abs().max().item()
+    if want_dx:
+        ref_dx = dh.float() @ w.float()
+        assert (dx.float() - ref_dx).abs().max().item() <= 0.01 * ref_dx.abs().max().item() + 0.02, \
+            (dx.float() - ref_dx).abs().max().item()
+
+
+def test_overlapped_exchange_matches_single_launch(monkeypatch):
+    """The communication CTAs inside the conv weight-gradient kernel + the trailing ranged step must produce
+    the same parameters / optimizer state as the classic single fused-step launch (same data, same seeds)."""
+    import numpy as np
+    from tf_yarn_b200 import keras
+
+    def run(overlap):
+        monkeypatch.setenv("TFY_OVERLAP", "1" if overlap else "0")
+        monkeypatch.setenv("TFY_OVERLAP_GROUPS", "20000")
+        torch.manual_seed(7)
+        m = _mnist_like(0.25, 0.5)
+        m.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True),
+                  optimizer=keras.optimizers.Adadelta(1.0))
+        rs = np.random.RandomState(0)
+        x = torch.from_numpy(rs.rand(512, 28, 28, 1).astype("float32"))
+        y = torch.from_numpy(rs.randint(0, 10, 512).astype("int64"))
+        m.fit(x, y, batch_size=128, epochs=2, shuffle=False, verbose=0)
+        eng = m._engine
+        torch.cuda.synchronize()
+        return eng, eng.fused.master.clone(), eng.fused.s1.clone(), eng.fused.flat_params.clone()
+
+    eng0, m0, s0, p0 = run(False)
+    eng1, m1, s1, p1 = run(True)
+    assert eng1._ov_gmid > 0, "the overlap role was not selected"
+    # same formulas, but two instantiations of the update (FMA contraction may differ by an ulp)
+    torch.testing.assert_close(m1, m0, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(s1, s0, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(p1.float(), p0.float(), rtol=1e-2, atol=1e-4)
+    assert eng1.fused.step_count == eng0.fused.step_count == 8

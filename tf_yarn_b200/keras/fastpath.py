@@ -15,7 +15,7 @@ the step does not go through autograd at all:
 * weight gradients are written straight into the flat gradient buffer consumed by the fused
   reduce-scatter / optimizer / all-gather kernel (no ``grad += g`` accumulation launches).
 
-9 launches of our kernels + 2 cuBLAS GEMMs per MNIST-CNN step, against 53 for the autograd engine
+10 launches per MNIST-CNN step, all of them our kernels (no cuBLAS / cuDNN), against 53 for the autograd engine
 (profiles/launches_*.csv).  Layers or shapes outside the kernels' envelope fall back to cuDNN / cuBLAS +
 the element-wise fused kernels of ``tfy_nn.cu``; models outside the grammar use the autograd engine
 (:class:`GraphTrainEngine`).
@@ -51,6 +51,9 @@ native.declare("tfy_conv3x3_c32_wgrad_scratch_elems", [], restype=ctypes.c_size_
 native.declare("tfy_conv3x3_c1_wgrad_tc", [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_dgrad_unpool", [_vp, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_conv3x3_c32_wgrad_unpool", [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
+native.declare("tfy_conv3x3_c32_wgrad_unpool_ov", [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp])
+native.declare("tfy_conv3x3_c32_wgrad_spare_ctas", [_i, _i, _i])
+native.declare("tfy_dense_bwd", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_dense_head_scratch_elems", [_i, _i], restype=ctypes.c_size_t)
 native.declare("tfy_dense_head_fused", [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
                                         _i, _vp])
@@ -166,30 +169,20 @@ class FastSequentialEngine(GraphTrainEngine):
         self._hp = self.fused.hyper.data_ptr()
         self._k = 0
         self._acc32 = {}
-        self._side = torch.cuda.Stream(device=dev)
-        # Optimizer/collective overlap (opt-in experiment, TFY_OVERLAP_OPT=1): the Dense + head parameters (98 % of
-        # the bytes here) have final gradients as soon as the first Dense layer's backward GEMMs are done, so their
-        # reduce-scatter -> update -> all-gather can run on a side stream while the convolution backward continues
-        # and the conv parameters follow in a second, tiny launch (FusedShardedOptimizer.step(elem_range=...)).
-        # Numerically identical (GPU tests pass with it), but as a separate kernel on a side stream it LOSES:
-        # 88.1 vs 85.5 us per step on 1 GPU, 117.4 vs 105.9 us on 2 GPUs -- its 296 CTAs cannot all be resident next
-        # to the register-heavy persistent conv kernels, and the per-CTA cross-GPU barriers then wait for peers'
-        # CTAs that are not scheduled yet.  The overlap has to come from comm CTAs INSIDE the persistent kernels
-        # (guaranteed co-residency); the ranged step is the building block for that.
-        self._overlap_split = 0
-        self._first_dense_li = -1
-        if os.environ.get("TFY_OVERLAP_OPT", "0") == "1":
-            ids = [id(p) for p in self.params]
-            for li, st in enumerate(plan):
-                if st.kind in ("dense", "head"):
-                    w0 = st.layer.module.weight
-                    if li > 0 and id(w0) in ids:
-                        self._first_dense_li = li
-                        self._overlap_split = int(self.fused.offsets[ids.index(id(w0))])
-                    break
-            later = [st for st in plan[self._first_dense_li + 1:] if st.kind == "conv"] if self._first_dense_li > 0 else [1]
-            if later or self._overlap_split % 8 or self._overlap_split <= 0:
-                self._overlap_split, self._first_dense_li = 0, -1     # conv after dense: keep the single launch
+        # Gradient-exchange overlap (opt-in, TFY_OVERLAP=1): parameters whose gradients are final before the
+        # convolution weight-gradient kernel starts (every layer AFTER that convolution: for the MNIST-CNN the two
+        # Dense layers, 98 % of the bytes) can be reduce-scattered / updated / all-gathered by COMMUNICATION CTAs
+        # inside that kernel (ops/csrc/tfy_fused_step.cuh: tfy_overlap_role) on the 4 SMs its patch grid leaves
+        # idle, the trailing fused-step launch handling the rest.  Numerically equivalent (GPU test), but measured
+        # on 1 and 2 B200s it does not pay for this model (profiles/r2/overlap_role_r2.md): four SMs move ~8k of the
+        # 75k (N=2) / 19k (N=8) groups per rank inside the 17 us kernel, while the cost of the trailing launch is
+        # the LATENCY chain signal -> in-switch reduce -> store/ack -> signal (12.5 us for 320 parameters, 19.7 us
+        # for all 1.2 M at N=2), which a smaller range does not shorten.  Round 1's variant (a separate kernel on a
+        # side stream) lost for a different reason: no co-residency guarantee + graph fork/join cost.
+        self._overlap = os.environ.get("TFY_OVERLAP", "0") == "1"
+        self._ov_used = False
+        self._ov_gmid = 0
+        self._warned = set()
         self._conv_sync = torch.zeros(1024, dtype=torch.int32, device=dev)     # grid barrier of the wgrad kernel
         self._c1_acc = torch.zeros(16 * 320, dtype=torch.float32, device=dev)    # first-layer dW/db accumulator
         self._c1_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -226,6 +219,44 @@ class FastSequentialEngine(GraphTrainEngine):
         H, W, Cin = ly.input_shape_
         return (Cin == 32 and ly.filters == 64 and st.pool and st.relu and (H - 2) % 8 == 0 and (W - 2) % 8 == 0
                 and B % 2 == 0)
+
+    def _warn_once(self, key: str, msg: str) -> None:
+        if key not in self._warned:
+            self._warned.add(key)
+            import logging
+            logging.getLogger(__name__).warning(msg)
+
+    def _overlap_desc(self, li: int, B: int, H: int, W: int):
+        """Fused-step descriptor for the communication CTAs of conv stage ``li``'s weight-gradient kernel, or None.
+
+        Overlapped: shard-relative groups [g_mid, S/8) of EVERY rank (balanced), where g_mid*8 is at least the
+        flat offset of the first parameter of the layers after ``li`` (their gradients are final by now; rank 0's
+        shard starts with the still-pending convolution parameters).  The size of the overlapped part is bounded
+        by what ``n_cta`` SMs can move while the weight gradient runs (TFY_OVERLAP_GROUPS overrides)."""
+        fused = self.fused
+        if not self._overlap or self._ov_used or fused.zero_grads or fused.param_dtype != torch.bfloat16 \
+                or fused.grad_dtype != torch.bfloat16:
+            return None
+        n_cta = int(self.lib.tfy_conv3x3_c32_wgrad_spare_ctas(B, H, W))
+        later = [st for st in self.plan[li + 1:] if st.kind in ("conv", "dense", "head")]
+        if n_cta <= 0 or not later:
+            return None
+        ids = [id(p) for p in self.params]
+        first_later = later[0].layer.module.weight
+        if id(first_later) not in ids:
+            return None
+        e_split = int(fused.offsets[ids.index(id(first_later))])
+        groups = fused.shard_n // 8
+        g_split = (e_split + 7) // 8
+        if g_split >= groups:
+            return None                              # rank 0's shard is all pending parameters: nothing balanced to take
+        budget = int(os.environ.get("TFY_OVERLAP_GROUPS", str(2000 * n_cta)))
+        g_mid = max(g_split, groups - budget)
+        if groups - g_mid < 64:
+            return None
+        ov = fused.overlap_step(g_mid, groups, n_cta)
+        self._ov_used, self._ov_gmid = True, g_mid
+        return ov
 
     def _host_loss_ptr(self):
         """Pinned scalar of the slot being captured: the head kernel stores the loss there directly (UVA), so the
@@ -407,9 +438,6 @@ class FastSequentialEngine(GraphTrainEngine):
         grad = None
         pre_gated = False          # the dgrad kernel of the next layer already applied this layer's ReLU gate
         dense_gated = False        # the fused head already produced the gated gradient + db of the Dense below
-        side_used = False
-        split_step = False
-        keep = []
         for li in range(len(self.plan) - 1, -1, -1):
             st = self.plan[li]
             sv = saved[li]
@@ -434,28 +462,21 @@ class FastSequentialEngine(GraphTrainEngine):
                                                         None, grad.data_ptr(), scale, B, ly.units,
                                                         self._partial.data_ptr(), b.grad.data_ptr(),
                                                         self._counter.data_ptr(), s), "act_drop_bwd_bias")
-                if first or os.environ.get("TFY_SIDE_STREAM") != "1":
+                I = xin.shape[1]
+                if (B <= 128 and ly.units <= 128 and ly.units % 8 == 0 and I % 8 == 0 and grad.is_contiguous()
+                        and xin.is_contiguous() and w.is_contiguous() and w.grad.is_contiguous()
+                        and os.environ.get("TFY_NO_TC_DENSE_BWD") != "1"):
+                    # dW = dh^T x (straight into the flat gradient buffer) and dx = dh W in ONE tcgen05 kernel
+                    dx = torch.empty((B, I), dtype=bf16, device=grad.device) if not first else None
+                    self._chk(lib.tfy_dense_bwd(grad.data_ptr(), xin.data_ptr(), w.data_ptr(), w.grad.data_ptr(),
+                                                dx.data_ptr() if dx is not None else None, B, ly.units, I, s),
+                              "dense_bwd")
+                    grad = dx
+                else:
+                    self._warn_once(f"dense_bwd:{li}", f"Dense layer {li} ({I} -> {ly.units}, batch {B}) is outside "
+                                    "the tcgen05 dense-backward kernel's envelope: cuBLAS computes dW / dx")
                     torch.mm(grad.t(), xin, out=w.grad)
                     grad = torch.mm(grad, w) if not first else None
-                else:
-                    # opt-in experiment: the weight-gradient GEMM is only consumed by the optimizer step, so it
-                    # can run on a side stream (a fork/join branch of the captured graph) next to the
-                    # data-gradient GEMM.  Measured: 109.7 vs 101.5 us per step -- the fork/join costs more than
-                    # the overlap of two 4 us GEMMs buys, so it stays off.
-                    cur_stream = torch.cuda.current_stream()
-                    self._side.wait_stream(cur_stream)
-                    with torch.cuda.stream(self._side):
-                        torch.mm(grad.t(), xin, out=w.grad)
-                    keep.append(grad)                       # no block reuse before the join
-                    side_used = True
-                    grad = torch.mm(grad, w)
-                if li == self._first_dense_li:
-                    # every Dense/head gradient is final and nothing reads those weights any more in this step
-                    self._side.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(self._side):
-                        self.fused.step(elem_range=(self._overlap_split, self.fused.n), advance=False, block=128)
-                    side_used = True
-                    split_step = True
             elif st.kind == "flatten":
                 if grad is not None:
                     grad = grad.reshape(sv)
@@ -485,10 +506,12 @@ class FastSequentialEngine(GraphTrainEngine):
                     if "wgrad_scratch" not in self._acc32:
                         self._acc32["wgrad_scratch"] = torch.empty(
                             int(lib.tfy_conv3x3_c32_wgrad_scratch_elems()), dtype=torch.float32, device=grad.device)
-                    self._chk(lib.tfy_conv3x3_c32_wgrad_unpool(
+                    ov = self._overlap_desc(li, B, H, W)
+                    self._chk(lib.tfy_conv3x3_c32_wgrad_unpool_ov(
                         xin.data_ptr(), grad.data_ptr(), aux.data_ptr(), scale,
                         self._acc32["wgrad_scratch"].data_ptr(), w.grad.data_ptr(), b.grad.data_ptr(),
-                        self._conv_sync.data_ptr(), B, H, W, s), "conv3x3_c32_wgrad_unpool")
+                        self._conv_sync.data_ptr(), B, H, W, ctypes.byref(ov) if ov is not None else None, s),
+                        "conv3x3_c32_wgrad_unpool")
                     dp = grad
                     grad = None
                     if not first:
@@ -552,11 +575,10 @@ class FastSequentialEngine(GraphTrainEngine):
                     if not first:
                         g = dx.permute(0, 2, 3, 1)
                         grad = g if g.is_contiguous() else g.contiguous()
-        if side_used:
-            torch.cuda.current_stream().wait_stream(self._side)
-        keep.clear()
-        if split_step:
-            self.fused.step(elem_range=(0, self._overlap_split), advance=True)
+        if self._ov_used:
+            # the communication CTAs of the weight-gradient kernel already handled groups [g_mid, end) of every shard
+            self.fused.step(shard_groups=(0, self._ov_gmid), advance=True)
+            self._ov_used = False
         else:
             self.fused.step()
         self._launches_per_step = self._k + 1     # our kernels launched per step (library GEMMs excluded)

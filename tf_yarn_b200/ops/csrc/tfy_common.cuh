@@ -83,6 +83,87 @@ __device__ __forceinline__ void tfy_block_barrier(const TfyCommCtx& c) {
 }
 
 // ---------------------------------------------------------------------------
+// Grid-level cross-GPU barriers (K2/K3/K4).  Measured on 2xB200 (gpurun_out/r2g_comm_sweep_N2.json, launches
+// captured in a CUDA graph): a kernel that only runs tfy_block_barrier costs 3.8 us with 1 CTA but 6.5 / 7.2 us
+// with 16 / 148 CTAs -- every CTA pays its own system-scope release and its own NVLink hop -- and the fused step
+// ran two of them.  What the collectives need is weaker:
+//   entry: "every rank has STARTED this kernel" (its inputs are complete by stream order).  ONE signal per rank
+//          pair, sent by CTA 0; every CTA polls the LOCAL pad.
+//   exit : "every rank's stores have landed".  Each CTA fences its own stores and arrives on a local counter;
+//          the LAST CTA signals the peers once and waits for their signals, so the grid cannot complete before
+//          the data of all peers is in place.  Other CTAs leave at once (or also wait, `all_wait`, when they
+//          go on to overwrite inputs the peers were reading).
+// Epochs: one monotonic counter per slot in local memory, bumped by the CTA that finishes last (CUDA-graph
+// replay safe).  Grids need not be co-resident.
+// ---------------------------------------------------------------------------
+#define TFY_SLOT_GRID_ENTRY 1008u
+#define TFY_SLOT_GRID_EXIT 1009u
+#define TFY_SLOT_GRID_SCRATCH 1010u     // epoch words used as local counters: [0] arrive, [1] finish
+
+__device__ __forceinline__ uint32_t tfy_grid_epoch(const TfyCommCtx& c) {
+    return *reinterpret_cast<volatile uint32_t*>(c.epoch + TFY_SLOT_GRID_ENTRY * TFY_MAX_RANKS) + 1u;
+}
+
+__device__ __forceinline__ void tfy_grid_poll(const TfyCommCtx& c, uint32_t slot, uint32_t e) {
+    if ((int)threadIdx.x < c.world) {
+        const uint32_t* mine =
+            reinterpret_cast<const uint32_t*>(c.peer_base[c.rank]) + slot * TFY_MAX_RANKS + threadIdx.x;
+        while ((int32_t)(tfy_ld_acquire_sys(mine) - e) < 0) {
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void tfy_grid_signal(const TfyCommCtx& c, uint32_t slot) {
+    if ((int)threadIdx.x < c.world) {
+        uint32_t* remote =
+            reinterpret_cast<uint32_t*>(c.peer_base[threadIdx.x]) + slot * TFY_MAX_RANKS + c.rank;
+        tfy_red_release_sys_inc(remote);
+    }
+}
+
+// all threads of all CTAs; e = tfy_grid_epoch(c) read at kernel start
+__device__ __forceinline__ void tfy_grid_entry(const TfyCommCtx& c, uint32_t e) {
+    if (blockIdx.x == 0) tfy_grid_signal(c, TFY_SLOT_GRID_ENTRY);
+    tfy_grid_poll(c, TFY_SLOT_GRID_ENTRY, e);
+}
+
+__device__ __forceinline__ void tfy_grid_exit(const TfyCommCtx& c, uint32_t e, bool all_wait) {
+    __shared__ uint32_t s_last;
+    __syncthreads();                                   // every thread of the CTA has issued its stores
+    if (threadIdx.x == 0) {
+        __threadfence_system();                        // ... and they are performed (peer replicas included)
+        uint32_t prev;
+        uint32_t* cnt = c.epoch + TFY_SLOT_GRID_SCRATCH * TFY_MAX_RANKS;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(cnt) : "memory");
+        s_last = (prev == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) tfy_grid_signal(c, TFY_SLOT_GRID_EXIT);
+    if (s_last || all_wait) tfy_grid_poll(c, TFY_SLOT_GRID_EXIT, e);
+}
+
+// last statement of the kernel (all CTAs): the CTA that finishes last bumps the epochs and clears the counters
+__device__ __forceinline__ bool tfy_grid_finish(const TfyCommCtx& c, uint32_t e) {
+    __shared__ uint32_t s_fin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        uint32_t* scratch = c.epoch + TFY_SLOT_GRID_SCRATCH * TFY_MAX_RANKS;
+        const uint32_t prev = atomicAdd(scratch + 1, 1u);
+        s_fin = (prev == gridDim.x - 1) ? 1u : 0u;
+        if (s_fin) {
+            c.epoch[TFY_SLOT_GRID_ENTRY * TFY_MAX_RANKS] = e;
+            c.epoch[TFY_SLOT_GRID_EXIT * TFY_MAX_RANKS] = e;
+            scratch[0] = 0u;
+            scratch[1] = 0u;
+        }
+    }
+    __syncthreads();
+    return s_fin != 0u;
+}
+
+// ---------------------------------------------------------------------------
 // 16-byte vector helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint4 tfy_ld16(const void* p) {

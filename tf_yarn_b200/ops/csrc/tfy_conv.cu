@@ -33,6 +33,7 @@
 #include <cuda.h>
 
 #include "tfy_common.cuh"
+#include "tfy_fused_step.cuh"
 
 namespace {
 
@@ -187,11 +188,13 @@ __device__ __forceinline__ uint8_t* c_align1024(uint8_t* p) {
 // tile row, tile column) incrementally -- no integer division per patch in the hot loops.
 struct CPatchIter {
     int tx, ty, bz, sx, sy, sb, tiles_x, tiles_y;
-    __device__ __forceinline__ CPatchIter(int tiles_x_, int tiles_y_) : tiles_x(tiles_x_), tiles_y(tiles_y_) {
+    // n_cta: CTAs sharing the patch list (the whole grid unless the kernel carries extra communication CTAs)
+    __device__ __forceinline__ CPatchIter(int tiles_x_, int tiles_y_, int n_cta = (int)gridDim.x)
+        : tiles_x(tiles_x_), tiles_y(tiles_y_) {
         const int tiles = tiles_x * tiles_y;
         int p = (int)blockIdx.x;
         bz = p / tiles; p -= bz * tiles; ty = p / tiles_x; tx = p - ty * tiles_x;
-        int q = (int)gridDim.x;
+        int q = n_cta;
         sb = q / tiles; q -= sb * tiles; sy = q / tiles_x; sx = q - sy * tiles_x;
     }
     __device__ __forceinline__ void next() {
@@ -597,7 +600,18 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
                          float* __restrict__ partials, __nv_bfloat16* __restrict__ dw, uint32_t* __restrict__ sync,
                          int tiles_x, int tiles_y, int n_patches, const __nv_bfloat16* __restrict__ dp,
                          const uint8_t* __restrict__ code, float scale, __nv_bfloat16* __restrict__ db, int PH,
-                         int PWp) {
+                         int PWp, const __grid_constant__ TfyOverlapStep ov) {
+    // The last ov.n_cta CTAs of the grid are COMMUNICATION CTAs: they run the fused reduce-scatter -> optimizer ->
+    // all-gather step of the parameters whose gradients were final before this kernel started (tfy_fused_step.cuh)
+    // over NVLink while the compute CTAs below run the weight gradient.  One CTA per SM and grid <= #SMs, so both
+    // roles are co-resident by construction.
+    const int n_cmp = (int)gridDim.x - ov.n_cta;                     // compute CTAs (share patches, grid barrier)
+    if ((int)blockIdx.x >= n_cmp) {
+        extern __shared__ uint8_t smem_role[];
+        tfy_pdl_sync();
+        tfy_overlap_role<WG_THREADS>(ov, (int)blockIdx.x - n_cmp, c_align1024(smem_role));
+        return;
+    }
     extern __shared__ uint8_t smem_raw[];
     C_TIMELINE_BEGIN();
     uint8_t* stages = c_align1024(smem_raw);        // [4] { dz [8 h][2 n][8 w][128 B] sw128 ; a [10 h][2 n][10 w][64 B] sw64 }
@@ -623,11 +637,11 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
     tfy_pdl_sync();                      // upstream grids complete; our dependents may start launching
     if (threadIdx.x == 0) C_MARK(1);
     const uint32_t gen0 = threadIdx.x == 0 ? *reinterpret_cast<volatile uint32_t*>(sync) : 0u;
-    const int my_patches = ((int)blockIdx.x < n_patches) ? (n_patches - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int my_patches = ((int)blockIdx.x < n_patches) ? (n_patches - 1 - (int)blockIdx.x) / n_cmp + 1 : 0;
 
     if (warp == WG_WORK_WARPS + 1) {
         if (c_elect_one()) {
-            CPatchIter it(tiles_x, tiles_y);
+            CPatchIter it(tiles_x, tiles_y, n_cmp);
             for (int i = 0; i < my_patches; ++i, it.next()) {
                 const int s = i % WG_STAGES;
                 if (i >= WG_STAGES) c_mbar_wait(&empty[s], ((i / WG_STAGES) - 1) & 1);
@@ -682,7 +696,7 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
             const int ppy = pp >> 2, ppx = pp & 3;
             const int row0 = (ppy * 2 * 2 + n) * 8 + ppx * 2;
             float colacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            CPatchIter it(tiles_x, tiles_y);
+            CPatchIter it(tiles_x, tiles_y, n_cmp);
             if (t >> 8) it.next();
             for (int i = (t >> 8); i < my_patches; i += 4) {
                 // patches i and i + 2 (if any)
@@ -774,8 +788,8 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync + 32 + 32 * (blockIdx.x & 15u)) : "memory");
     }
     if (blockIdx.x == 0 && warp == 0) {
-        if (lane < 16 && lane < (int)gridDim.x) {
-            const uint32_t expect = (gridDim.x - (uint32_t)lane + 15u) / 16u;
+        if (lane < 16 && lane < n_cmp) {
+            const uint32_t expect = ((uint32_t)n_cmp - (uint32_t)lane + 15u) / 16u;
             volatile uint32_t* cnt = sync + 32 + 32 * lane;
             while (*cnt != expect) __nanosleep(20);
             *cnt = 0u;
@@ -794,10 +808,10 @@ tfy_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz, const __gri
     if (threadIdx.x == 0) C_MARK(8);
     // slice of the outputs owned by this CTA (float4 units), summed over the partials in a fixed order
     constexpr int TOTAL4 = (UNPOOL ? WG_PART : WG_OUT) / 4, STRIDE4 = WG_PART / 4;
-    const int per = (TOTAL4 + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int per = (TOTAL4 + n_cmp - 1) / n_cmp;
     const int lo = (int)blockIdx.x * per, hi = min(lo + per, TOTAL4);
     const int len = max(hi - lo, 0);
-    const int n_part = (int)gridDim.x;                               // every CTA wrote a partial
+    const int n_part = n_cmp;                                       // every CTA wrote a partial
     const float4* src = reinterpret_cast<const float4*>(partials) + lo;
     auto store = [&](int f, const float4& s4) {
         __nv_bfloat162 l2 = __floats2bfloat162_rn(s4.x, s4.y), h2 = __floats2bfloat162_rn(s4.z, s4.w);
@@ -1286,7 +1300,7 @@ int tfy_conv3x3_c32_wgrad(const void* a, const void* dz, float* partials, void* 
     const int tiles_x = OW / 8, tiles_y = OH / 8, n_patches = tiles_x * tiles_y * (B / 2);
     tfy_launch_pdl((tfy_conv3x3_wgrad_kernel<false>), dim3(c_grid(n_patches)), dim3(WG_THREADS), WG_SMEM, s, mz, ma,
                    partials, (__nv_bfloat16*)dw, sync, tiles_x, tiles_y, n_patches, (const __nv_bfloat16*)nullptr,
-                   (const uint8_t*)nullptr, 1.0f, (__nv_bfloat16*)nullptr, 0, 0);
+                   (const uint8_t*)nullptr, 1.0f, (__nv_bfloat16*)nullptr, 0, 0, TfyOverlapStep{});
     return (int)cudaGetLastError();
 }
 
@@ -1305,19 +1319,44 @@ int tfy_conv3x3_c32_dgrad_unpool(const void* dp, const void* code, float scale, 
     return (int)cudaGetLastError();
 }
 
-// also writes db [64] = sum over batch and positions of the gated pooled gradient
-int tfy_conv3x3_c32_wgrad_unpool(const void* a, const void* dp, const void* code, float scale, float* partials,
-                                 void* dw, void* db, uint32_t* sync, int B, int H, int W, cudaStream_t s) {
+// also writes db [64] = sum over batch and positions of the gated pooled gradient.
+// ov (optional): a fused gradient-exchange/optimizer step to run on SPARE SMs next to the weight gradient
+// (tfy_overlap_role).  ov->n_cta is clamped to the SMs the compute grid leaves free (576 patches -> 144 compute
+// CTAs on a 148-SM B200 -> 4 communication CTAs); tfy_conv3x3_c32_wgrad_spare_ctas() tells the caller how many
+// that is so that it can size the overlapped range.
+int tfy_conv3x3_c32_wgrad_unpool_ov(const void* a, const void* dp, const void* code, float scale, float* partials,
+                                    void* dw, void* db, uint32_t* sync, int B, int H, int W, const TfyOverlapStep* ov,
+                                    cudaStream_t s) {
     const int OH = H - 2, OW = W - 2;
     if ((OH % 8) || (OW % 8) || (B % 2)) return -2;
     if (!c_init() || c_sms > 160) return -4;
     CUtensorMap ma;
     if (!c_map_nhwc(&ma, a, B, H, W, CIN, HALO, HALO)) return -6;
     const int tiles_x = OW / 8, tiles_y = OH / 8, n_patches = tiles_x * tiles_y * (B / 2);
-    tfy_launch_pdl((tfy_conv3x3_wgrad_kernel<true>), dim3(c_grid(n_patches)), dim3(WG_THREADS), WG_SMEM, s, ma, ma,
+    const int n_cmp = c_grid(n_patches);
+    TfyOverlapStep o{};
+    if (ov != nullptr && ov->n_cta > 0) {
+        o = *ov;
+        if (o.n_cta > c_sms - n_cmp) return -7;       // the role must not displace a compute CTA
+        if (o.slot0 < 0 || o.slot0 + o.n_cta > TFY_MAX_BLOCKS) return -8;
+    }
+    tfy_launch_pdl((tfy_conv3x3_wgrad_kernel<true>), dim3(n_cmp + o.n_cta), dim3(WG_THREADS), WG_SMEM, s, ma, ma,
                    partials, (__nv_bfloat16*)dw, sync, tiles_x, tiles_y, n_patches, (const __nv_bfloat16*)dp,
-                   (const uint8_t*)code, scale, (__nv_bfloat16*)db, OH / 2, OW / 2);
+                   (const uint8_t*)code, scale, (__nv_bfloat16*)db, OH / 2, OW / 2, o);
     return (int)cudaGetLastError();
+}
+
+int tfy_conv3x3_c32_wgrad_unpool(const void* a, const void* dp, const void* code, float scale, float* partials,
+                                 void* dw, void* db, uint32_t* sync, int B, int H, int W, cudaStream_t s) {
+    return tfy_conv3x3_c32_wgrad_unpool_ov(a, dp, code, scale, partials, dw, db, sync, B, H, W, nullptr, s);
+}
+
+// SMs the weight-gradient grid leaves idle for B images of H x W (0 when the patches fill every SM)
+int tfy_conv3x3_c32_wgrad_spare_ctas(int B, int H, int W) {
+    if (!c_init()) return 0;
+    const int n_patches = ((W - 2) / 8) * ((H - 2) / 8) * (B / 2);
+    const int spare = c_sms - c_grid(n_patches);
+    return spare > 0 ? spare : 0;
 }
 
 // First-layer (C_in = 1, 32 filters) forward with bias + ReLU.  x: [B, H, W, 1] fp32 or bf16, w: [32, 3, 3, 1] bf16,

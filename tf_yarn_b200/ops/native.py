@@ -48,6 +48,27 @@ class OptHyper(ctypes.Structure):
     ]
 
 
+class OverlapStep(ctypes.Structure):
+    """Mirror of TfyOverlapStep (ops/csrc/tfy_fused_step.cuh): a fused gradient-exchange / optimizer step that the
+    communication CTAs of a persistent compute kernel run next to the compute."""
+    _fields_ = [
+        ("c", CommCtx),
+        ("grad_off", ctypes.c_uint64),
+        ("param_off", ctypes.c_uint64),
+        ("shard_n", ctypes.c_size_t),
+        ("master", ctypes.c_void_p),
+        ("s1", ctypes.c_void_p),
+        ("s2", ctypes.c_void_p),
+        ("hp", ctypes.c_void_p),
+        ("g0", ctypes.c_size_t),
+        ("g1", ctypes.c_size_t),
+        ("opt", ctypes.c_int32),
+        ("mode", ctypes.c_int32),
+        ("n_cta", ctypes.c_int32),
+        ("slot0", ctypes.c_int32),
+    ]
+
+
 _lib: Optional[ctypes.CDLL] = None
 _lock = threading.Lock()
 
@@ -78,6 +99,9 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.tfy_fused_step.argtypes = [ctxp, i, i, i, i, u64, u64, sz, vp, vp, vp, vp, i, i, i, vp]
     if hasattr(lib, "tfy_fused_step_range"):
         lib.tfy_fused_step_range.argtypes = [ctxp, i, i, i, i, u64, u64, sz, vp, vp, vp, vp, i, i, i, sz, sz, i, vp]
+    if hasattr(lib, "tfy_fused_step_shard_range"):
+        lib.tfy_fused_step_shard_range.argtypes = [ctxp, i, i, i, i, u64, u64, sz, vp, vp, vp, vp, i, i, i, sz, sz, i,
+                                                   vp]
     for name, (args, restype) in _EXTRA_DECLS.items():
         fn = getattr(lib, name, None)
         if fn is not None:

@@ -367,13 +367,23 @@ class FusedShardedOptimizer:
 
     # -- the hot path --------------------------------------------------------
     def step(self, stream=None, elem_range: Optional[Tuple[int, int]] = None, advance: bool = True,
-             block: int = 0) -> None:
+             block: int = 0, shard_groups: Optional[Tuple[int, int]] = None) -> None:
         """One fused update.  ``elem_range=(e0, e1)`` restricts it to that element range of the flat buffers
         (multiples of 8): a step may be split into several launches -- e.g. the gradients that are final
         early on a side stream while backward continues -- with ``advance=True`` on the LAST one only, so
-        that every launch of the step sees the same step counter."""
+        that every launch of the step sees the same step counter.  ``shard_groups=(g0, g1)`` restricts it to
+        groups of 8 elements RELATIVE TO EVERY RANK'S SHARD (the complement of :meth:`overlap_step`)."""
         c = self.comm
-        if elem_range is None and advance:
+        if shard_groups is not None:
+            if self.zero_grads:
+                raise ValueError("ranged steps do not clear gradients: construct with zero_grads=False")
+            g0, g1 = shard_groups
+            rc = c.lib.tfy_fused_step_shard_range(
+                c.arena.ctx_ref, _DT[self.grad_dtype], _DT[self.param_dtype], self.spec.code, c.mode,
+                self.grad_off, self.param_off, self.shard_n,
+                self.master.data_ptr(), self.s1.data_ptr(), self.s2.data_ptr(), self.hyper.data_ptr(),
+                0, 0, int(block), int(g0), int(g1), int(advance), _stream_ptr(stream))
+        elif elem_range is None and advance:
             rc = c.lib.tfy_fused_step(
                 c.arena.ctx_ref, _DT[self.grad_dtype], _DT[self.param_dtype], self.spec.code, c.mode,
                 self.grad_off, self.param_off, self.shard_n,
@@ -392,6 +402,24 @@ class FusedShardedOptimizer:
                 0, 0, int(block), e0, e1, int(advance), _stream_ptr(stream))
         native.check(rc, "tfy_fused_step")
         c.launches += 1
+
+    def overlap_step(self, g0: int, g1: int, n_cta: int, slot0: int = 960):
+        """Descriptor of the fused step of shard-relative groups ``[g0, g1)`` for the communication CTAs of a
+        persistent compute kernel (``tfy_conv3x3_c32_wgrad_unpool_ov``): they reduce-scatter, update and
+        all-gather those parameters over NVLink WHILE the kernel's compute CTAs run, so that part of the
+        gradient exchange costs no step time.  bf16 gradients / parameters only.  The trailing
+        ``step(shard_groups=(0, g0))`` of the same training step publishes the result (its exit barrier)."""
+        if self.grad_dtype != torch.bfloat16 or self.param_dtype != torch.bfloat16:
+            raise ValueError("overlap_step needs bf16 gradients and parameters")
+        c = self.comm
+        ov = native.OverlapStep()
+        ov.c = c.arena.ctx
+        ov.grad_off, ov.param_off, ov.shard_n = self.grad_off, self.param_off, self.shard_n
+        ov.master, ov.s1, ov.s2 = self.master.data_ptr(), self.s1.data_ptr(), self.s2.data_ptr()
+        ov.hp = self.hyper.data_ptr()
+        ov.g0, ov.g1 = int(g0), int(min(g1, self.shard_n // 8))
+        ov.opt, ov.mode, ov.n_cta, ov.slot0 = self.spec.code, c.mode, int(n_cta), int(slot0)
+        return ov
 
     # -- checkpoint support ----------------------------------------------------
     def gather_state(self) -> dict:
