@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--graph", action="store_true", help="standin: capture the step (NCCL included) in a CUDA graph")
     ap.add_argument("--no-exposed", action="store_true", help="ours: skip the LOCAL-mode run behind exposed_comm_ms")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch of the secondary configs (0 = default)")
+    ap.add_argument("--side-tasks", action="store_true", help="bert: keep the TensorBoard side task alive during the run")
     args = ap.parse_args()
     if args.config == "mnist":
         if args.impl == "reference":

@@ -64,13 +64,14 @@ def _ensure_installed() -> str:
 # ------------------------------------------------------------------------------------------------------
 # user side: the experiment (pickled by value with cloudpickle; runs inside the reference's worker)
 # ------------------------------------------------------------------------------------------------------
-def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int):
+def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int, config: str = "mnist", batch: int = 0):
     def experiment_fn():
+        import argparse
         import torch
         import torch.nn as nn
         import torch.nn.functional as F
         from tf_yarn.pytorch import DataLoaderArgs, DistributedDataParallelArgs, PytorchExperiment
-        from bench import common, mnist
+        from bench import common, mnist, models
 
         class Net(nn.Module):            # reference: tf_yarn/examples/pytorch/pytorch_distributed_example.py:44-67
             def __init__(self):
@@ -92,15 +93,29 @@ def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int):
                 x = self.dropout2(x)
                 return F.log_softmax(self.fc2(x), dim=1)
 
-        B, NB = mnist.PER_GPU_BATCH, mnist.POOL_BATCHES
         rank = int(os.environ.get("RANK", 0))
+        if config == "mnist":
+            B, NB = mnist.PER_GPU_BATCH, mnist.POOL_BATCHES
+            make_net = lambda: Net().to(memory_format=torch.channels_last)                  # noqa: E731
+            make_pool = lambda: mnist.make_pool(seed=100 + rank, nhwc=False)                  # noqa: E731
+            make_opt = lambda ps: torch.optim.Adadelta(ps, lr=1.0 * world, rho=0.95, eps=1e-7)  # noqa: E731
+            loss_of = lambda out, yb: F.nll_loss(out.float(), yb)                             # noqa: E731
+            h2d = B * (784 * 4 + 8)
+        else:                                                                               # resnet50 (config 4)
+            import torchvision
+            B, NB = batch or models.RESNET_BATCH, models.RESNET_POOL
+            make_net = lambda: torchvision.models.resnet50().to(memory_format=torch.channels_last)  # noqa: E731
+            make_pool = lambda: models.resnet_pool(rank, pinned=False)                        # noqa: E731
+            make_opt = lambda ps: torch.optim.SGD(ps, lr=0.01, momentum=0.9)                   # noqa: E731
+            loss_of = lambda out, yb: F.cross_entropy(out.float(), yb)                        # noqa: E731
+            h2d = B * (3 * 224 * 224 * 4 + 8)
 
         class BatchPool(torch.utils.data.Dataset):
             """Pre-batched, pre-pinned pool: item i is batch i (the friendliest input the DataLoader can get:
             no per-sample collation, `pin_memory` finds the tensors already pinned)."""
 
             def __init__(self):
-                x, y = mnist.make_pool(seed=100 + rank, nhwc=False)
+                x, y = make_pool()
                 self.x, self.y = x.pin_memory(), y.pin_memory()
 
             def __len__(self):
@@ -114,7 +129,7 @@ def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int):
             torch.cuda.set_device(device)
             dev = torch.device(device)
             params = [p for p in ddp_model.parameters()]
-            opt = torch.optim.Adadelta(params, lr=1.0 * world, rho=0.95, eps=1e-7)
+            opt = make_opt(params)
             ds = trainloader.dataset
             local = dev.index or 0
             sampler = common.ClockSampler(local)
@@ -124,13 +139,15 @@ def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int):
                 opt.zero_grad(set_to_none=True)
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     out = ddp_model(xb)
-                loss = F.nll_loss(out.float(), yb)
+                loss = loss_of(out, yb)
                 loss.backward()            # DDP all-reduces the 25 MB buckets (NCCL) during backward
                 opt.step()
                 return loss
 
             # device-timed: the pool resident in HBM (as in the `ours` arm)
             x_dev, y_dev = ds.x.to(dev), ds.y.to(dev)
+            if x_dev.dim() == 4:
+                x_dev = x_dev.contiguous(memory_format=torch.channels_last)
             state = {"b": 0}
 
             def run(n):
@@ -149,7 +166,7 @@ def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int):
 
             # end to end: the reference's DataLoader (DistributedSampler, pinned batches) -> H2D -> step -> loss.item()
             it = {"it": iter(trainloader)}
-            last = {"loss": float("nan"), "first": None}
+            last = {"loss": float("nan")}
 
             def next_batch():
                 try:
@@ -162,10 +179,10 @@ def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int):
                 for _ in range(steps):
                     xb, yb = next_batch()
                     xb = xb.to(dev, non_blocking=True)
+                    if xb.dim() == 4 and config != "mnist":
+                        xb = xb.contiguous(memory_format=torch.channels_last)
                     yb = yb.to(dev, non_blocking=True)
                     last["loss"] = step(xb, yb).item()
-                    if last["first"] is None:
-                        last["first"] = last["loss"]
 
             e2e_region()
             e2e_ms = common.wall_regions(world, repeats, e2e_region)
@@ -173,13 +190,24 @@ def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int):
             flat = torch.cat([p.detach().reshape(-1) for p in params])
             in_sync = common.all_ranks_equal(common.tensor_checksum(flat), world)
             if rank == 0:
-                out = mnist.base_record(world, steps, warm, repeats, ms_per_step, "reference", clocks, {
-                    "model": "the reference's PyTorch worker (tf_yarn.pytorch.tasks.worker._train, unmodified): "
-                             "torch DistributedDataParallel (bucket_cap_mb=25) over NCCL, MNIST-CNN (1,199,882 "
-                             "params), autocast bf16, torch.optim.Adadelta(1.0*size), eager",
-                    "same_config": True, "cuda_graph": False})
-                out["e2e"] = {"value": world * B / (e2e_ms_per_step * 1e-3), "unit": "samples/s",
-                              "h2d_bytes_per_step": B * (784 * 4 + 8), "d2h_bytes_per_step": 4, "steps": steps,
+                if config == "mnist":
+                    out = mnist.base_record(world, steps, warm, repeats, ms_per_step, "reference", clocks, {
+                        "model": "the reference's PyTorch worker (tf_yarn.pytorch.tasks.worker._train, unmodified): "
+                                 "torch DistributedDataParallel (bucket_cap_mb=25) over NCCL, MNIST-CNN (1,199,882 "
+                                 "params), autocast bf16, torch.optim.Adadelta(1.0*size), eager",
+                        "same_config": True, "cuda_graph": False})
+                    unit = "samples/s"
+                else:
+                    ns = argparse.Namespace(config="resnet50", steps=steps)
+                    out = models._record(
+                        "images/sec, PytorchExperiment ResNet-50 DistributedDataParallel (whole job)", "images/s", world,
+                        ns, warm, repeats, ms_per_step, B, "reference", clocks,
+                        "the reference's PyTorch worker (tf_yarn.pytorch.tasks.worker._train, unmodified): torchvision "
+                        "ResNet-50 under torch DistributedDataParallel (bucket_cap_mb=25) over NCCL, autocast bf16, "
+                        "torch.optim.SGD(momentum 0.9), eager", {"same_config": True})
+                    unit = "images/s"
+                out["e2e"] = {"value": world * B / (e2e_ms_per_step * 1e-3), "unit": unit,
+                              "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": steps,
                               "repeats": repeats, "ms_per_step": e2e_ms_per_step, "final_loss": last["loss"]}
                 out["gpu_launches"] = 0
                 out["params_in_sync"] = in_sync
@@ -187,7 +215,7 @@ def make_experiment_fn(steps: int, warmup: int, repeats: int, world: int):
                 common.emit(out)
 
         return PytorchExperiment(
-            model=Net().to(memory_format=torch.channels_last),
+            model=make_net(),
             main_fn=main_fn,
             train_dataset=BatchPool(),
             # batch_size=None: the dataset yields whole batches; prefetch_factor must be None with num_workers=0
@@ -252,8 +280,9 @@ def run_reference(args) -> int:
     client = skein.ApplicationClient.from_current()
     if rank == 0:
         from bench.common import pick_repeats
-        repeats_n = pick_repeats(args.steps, args.repeats)
-        fn = make_experiment_fn(args.steps, args.warmup, repeats_n, world)
+        cfg = getattr(args, "config", "mnist")
+        repeats_n = pick_repeats(args.steps, args.repeats or (3 if cfg != "mnist" else 0))
+        fn = make_experiment_fn(args.steps, args.warmup, repeats_n, world, cfg, getattr(args, "batch", 0))
         client.kv[constants.KV_EXPERIMENT_FN] = cloudpickle.dumps(fn)
     torch.cuda.set_device(local)
     ref_worker._train(local, rank, world, "nccl")

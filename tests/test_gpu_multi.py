@@ -45,3 +45,10 @@ def test_headline_bench_ranks_stay_in_sync():
     assert rec["params_in_sync"] is True
     assert rec["e2e"]["loss_fell"] is True
     assert rec["gpu_launches"] > 0
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_ddp_wrapper_matches_torch_ddp():
+    n = min(_ngpu(), 8)
+    res = _torchrun(n, ["tests/gpu/ddp_check.py"], 29613)
+    assert res.returncode == 0 and "DDP CHECK OK" in res.stdout, res.stdout[-4000:]

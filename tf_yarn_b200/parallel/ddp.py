@@ -7,11 +7,15 @@ arguments tf_yarn/pytorch/experiment.py:23-27):
 * parameters are bucketed in reverse registration order (first bucket 1 MiB,
   then ``bucket_cap_mb``) into flat gradient buffers that live in the
   symmetric arena; every ``p.grad`` is a view into its bucket;
-* a post-accumulate-grad hook counts ready gradients; when a bucket is
-  complete its all-reduce kernel (``multimem.ld_reduce`` + ``multimem.st``,
-  averaged, in place) is launched on a side stream, overlapping the rest of
-  backward;
-* at the end of backward the compute stream waits for the side stream;
+* a post-accumulate-grad hook makes ONE call per parameter into the native
+  reducer (``ops/csrc/tfy_reducer.cpp``): it counts ready gradients and, when a
+  bucket (and all its predecessors) is complete, launches the bucket's
+  all-reduce kernel (``multimem.ld_reduce`` + ``multimem.st``, averaged, in
+  place) on its communication stream, overlapping the rest of backward;
+* :meth:`DistributedDataParallel.fuse_optimizer` replaces the per-bucket
+  all-reduce by the fused reduce-scatter -> optimizer -> all-gather kernel
+  (K4), so the optimizer step overlaps backward as well;
+* at the end of backward the compute stream waits for the last collective;
 * parameters (and, each forward, module buffers when ``broadcast_buffers``)
   are broadcast from rank 0 with the K7 kernel.
 
@@ -21,12 +25,23 @@ the plumbing configuration) :func:`wrap_model` returns torch's own DDP.
 from __future__ import annotations
 
 import contextlib
+import ctypes
 from typing import List, Optional
 
 import torch
 import torch.nn as nn
 
-from tf_yarn_b200.parallel.comm import Communicator
+from tf_yarn_b200.ops import native
+from tf_yarn_b200.parallel.comm import _DT, Communicator
+from tf_yarn_b200.parallel.optspec import OptimizerSpec
+
+_vp, _i, _u64, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t
+native.declare("tfy_reducer_create", [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i], restype=_vp)
+native.declare("tfy_reducer_set_fused", [_vp, _i, _i, _u64, _vp, _vp, _vp, _sz, _i, _i, _vp])
+native.declare("tfy_reducer_mark_ready", [_vp, _i, _vp])
+native.declare("tfy_reducer_finalize", [_vp, _vp])
+native.declare("tfy_reducer_launches", [_vp], restype=ctypes.c_long)
+native.declare("tfy_reducer_destroy", [_vp], restype=None)
 
 _FIRST_BUCKET_BYTES = 1 << 20
 
@@ -45,7 +60,8 @@ def _view_like(flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
 
 
 class _Bucket:
-    __slots__ = ("params", "offsets", "flat", "pending", "launched", "event", "dtype")
+    __slots__ = ("params", "offsets", "flat", "pending", "launched", "event", "dtype", "off", "pflat", "poff",
+                 "master", "s1", "s2", "hyper", "shard_n")
 
     def __init__(self, dtype):
         self.params: List[nn.Parameter] = []
@@ -76,6 +92,13 @@ class DistributedDataParallel(nn.Module):
         self._param_bucket = {}          # id(param) -> (bucket, index in bucket); tensors compare elementwise
         self._build_buckets(int(bucket_cap_mb) << 20)
         self._sync_params_and_buffers()
+        # native reducer (C++): needs the kernel library and a CUDA device; the Python bookkeeping below is the
+        # fallback for host-only unit tests with a fake communicator
+        self._reducer = None
+        self._fused = None
+        self._param_index = {}
+        if getattr(comm, "lib", None) is not None and torch.cuda.is_available():
+            self._create_reducer()
         for b in self._buckets:
             for p in b.params:
                 p.register_post_accumulate_grad_hook(self._make_hook(p))
@@ -103,12 +126,83 @@ class DistributedDataParallel(nn.Module):
             last = b.params[-1]
             n = b.offsets[-1] + (last.numel() + 7) // 8 * 8
             n = self.comm.pad_elems(n, b.dtype)
-            _, b.flat = self.comm.arena.empty((n,), b.dtype, align=4096)
+            b.off, b.flat = self.comm.arena.empty((n,), b.dtype, align=4096)
             b.flat.zero_()
             for i, (p, o) in enumerate(zip(b.params, b.offsets)):
                 p.grad = _view_like(b.flat, o, p)
                 self._param_bucket[id(p)] = (b, i)
             b.pending = len(b.params)
+
+    def _create_reducer(self) -> None:
+        nb = len(self._buckets)
+        offs = (ctypes.c_uint64 * nb)(*[b.off for b in self._buckets])
+        ns = (ctypes.c_size_t * nb)(*[b.flat.numel() for b in self._buckets])
+        dts = (ctypes.c_int * nb)(*[_DT[b.dtype] for b in self._buckets])
+        nps = (ctypes.c_int * nb)(*[len(b.params) for b in self._buckets])
+        flat_params, pb = [], []
+        for bi, b in enumerate(self._buckets):
+            for p in b.params:
+                self._param_index[id(p)] = len(flat_params)
+                flat_params.append(p)
+                pb.append(bi)
+        pbs = (ctypes.c_int * len(pb))(*pb)
+        lib = self.comm.lib
+        self._reducer = lib.tfy_reducer_create(self.comm.arena.ctx_ref, nb, offs, ns, dts, nps, len(pb), pbs,
+                                               self.comm.pick_algo_inplace())
+        if not self._reducer:
+            raise RuntimeError("tfy_reducer_create failed")
+
+    @property
+    def kernel_launches(self) -> int:
+        """Collective / fused-step kernels launched by the reducer so far."""
+        if self._reducer:
+            return int(self.comm.lib.tfy_reducer_launches(self._reducer))
+        return 0
+
+    def fuse_optimizer(self, kind: str = "sgd", **hyper):
+        """Move the optimizer INTO the gradient exchange: every bucket runs the fused reduce-scatter -> update
+        -> all-gather kernel (K4: ``multimem.ld_reduce`` of the owned 1/world shard, SGD-momentum / Adam / Adagrad /
+        Adadelta on fp32 master + sharded state, ``multimem.st`` of the new parameters) on the communication stream
+        as soon as its gradients are complete, so the whole optimizer step overlaps backward.  Parameters are
+        re-pointed at flat symmetric buffers.  Returns an optimizer-shaped object (``step`` / ``zero_grad`` are
+        no-ops: by the time backward returns, the update is queued behind it).  Gradient clipping between
+        ``backward()`` and ``step()`` is not available in this mode."""
+        if not self._reducer:
+            raise RuntimeError("fuse_optimizer needs the native reducer (CUDA)")
+        if self._fused is not None:
+            return self._fused
+        kinds = {"sgd": OptimizerSpec.sgd, "adam": OptimizerSpec.adam, "adagrad": OptimizerSpec.adagrad,
+                 "adadelta": OptimizerSpec.adadelta}
+        if kind not in kinds:
+            raise ValueError(f"unknown fused optimizer {kind!r}")
+        spec = kinds[kind](**hyper)
+        comm = self.comm
+        dev = f"cuda:{comm.device}"
+        world = comm.world
+        for bi, b in enumerate(self._buckets):
+            n = b.flat.numel()
+            b.shard_n = n // world
+            assert b.shard_n * world == n and b.shard_n % 8 == 0, (n, world)
+            b.poff, b.pflat = comm.arena.empty((n,), b.dtype, align=4096)
+            b.pflat.zero_()
+            for p, o in zip(b.params, b.offsets):
+                view = _view_like(b.pflat, o, p)
+                view.copy_(p.data)
+                p.data = view
+            r = comm.rank if world > 1 else 0
+            b.master = b.pflat[r * b.shard_n:(r + 1) * b.shard_n].float().clone()
+            b.s1 = torch.full((b.shard_n,), spec.init_s1, dtype=torch.float32, device=dev)
+            b.s2 = torch.zeros(b.shard_n if spec.n_states > 1 else 8, dtype=torch.float32, device=dev)
+            host = native.OptHyper(spec.lr, spec.p1, spec.p2, spec.eps, spec.weight_decay, 1.0, 0, spec.flags, 0, 0)
+            b.hyper = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(dev)
+            native.check(comm.lib.tfy_reducer_set_fused(
+                self._reducer, bi, _DT[b.dtype], b.poff, b.master.data_ptr(), b.s1.data_ptr(), b.s2.data_ptr(),
+                b.shard_n, spec.code, comm.mode, b.hyper.data_ptr()), "tfy_reducer_set_fused")
+        torch.cuda.current_stream().synchronize()
+        if world > 1:
+            comm.barrier()
+        self._fused = _FusedOptimizer(self, spec)
+        return self._fused
 
     def _sync_params_and_buffers(self) -> None:
         if self.comm.world == 1:
@@ -127,6 +221,7 @@ class DistributedDataParallel(nn.Module):
         bucket, idx = self._param_bucket[id(p)]
         off = bucket.offsets[idx]
         view = _view_like(bucket.flat, off, p)
+        pidx = self._param_index.get(id(p), -1)
 
         def hook(param: nn.Parameter) -> None:
             g = param.grad
@@ -139,6 +234,11 @@ class DistributedDataParallel(nn.Module):
             if not self._callback_queued:
                 self._callback_queued = True
                 torch.autograd.Variable._execution_engine.queue_callback(self._finalize_backward)
+            if self._reducer:
+                rc = self.comm.lib.tfy_reducer_mark_ready(self._reducer, pidx, torch.cuda.current_stream().cuda_stream)
+                if rc:
+                    raise RuntimeError(f"bucket collective failed to launch: {rc}")
+                return
             bucket.pending -= 1
             if bucket.pending == 0:
                 self._launch_ready_prefix()
@@ -170,6 +270,11 @@ class DistributedDataParallel(nn.Module):
 
     def _finalize_backward(self) -> None:
         self._callback_queued = False
+        if self._reducer:
+            rc = self.comm.lib.tfy_reducer_finalize(self._reducer, torch.cuda.current_stream().cuda_stream)
+            if rc:
+                raise RuntimeError(f"bucket collective failed to launch: {rc}")
+            return
         for b in self._buckets[self._next_bucket:]:
             # buckets still waiting for a predecessor, or whose parameters received no gradient this step
             # (they contribute zeros -- what find_unused_parameters=True does in torch DDP), in index order
@@ -202,14 +307,60 @@ class DistributedDataParallel(nn.Module):
             self.require_backward_grad_sync = old
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # keep the bucket views alive
+        if self._fused is not None and self.require_backward_grad_sync:
+            return                      # the fused kernel clears every bucket behind itself
         for b in self._buckets:
             b.flat.zero_()
             for p, o in zip(b.params, b.offsets):
                 p.grad = _view_like(b.flat, o, p)
 
+    def __del__(self):
+        try:
+            if getattr(self, "_reducer", None):
+                self.comm.lib.tfy_reducer_destroy(self._reducer)
+                self._reducer = None
+        except Exception:  # noqa: BLE001
+            pass
+
     # state_dict()/load_state_dict() are nn.Module's: keys carry the ``module.`` prefix exactly like
     # torch.nn.parallel.DistributedDataParallel, so checkpoints are interchangeable with the reference's
     # (tf_yarn/pytorch/model_ckpt.py saves ``model.module.state_dict()`` when it sees a wrapper).
+
+
+class _FusedOptimizer:
+    """Optimizer-shaped handle of :meth:`DistributedDataParallel.fuse_optimizer`."""
+
+    def __init__(self, ddp: "DistributedDataParallel", spec: OptimizerSpec):
+        self._ddp, self.spec = ddp, spec
+        self.param_groups = [{"lr": spec.lr, "params": [p for b in ddp._buckets for p in b.params]}]
+
+    def step(self, closure=None):
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self.spec.lr:                       # an LR scheduler changed it: 4-byte copies, graph/stream safe
+            self.set_lr(lr)
+        return None
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        return None
+
+    def set_lr(self, lr: float) -> None:
+        self.spec.lr = float(lr)
+        t = torch.tensor([lr], dtype=torch.float32).view(torch.uint8)
+        for b in self._ddp._buckets:
+            b.hyper[0:4].copy_(t, non_blocking=True)
+
+    def state_dict(self) -> dict:
+        comm = self._ddp.comm
+        out = {"kind": "tfy_fused_ddp", "buckets": []}
+        for b in self._ddp._buckets:
+            out["buckets"].append({"master": b.master.cpu(), "s1": b.s1.cpu(), "s2": b.s2.cpu(),
+                                   "step": int(b.hyper[24:28].view(torch.int32).item()), "rank": comm.rank})
+        return out
+
+    def load_state_dict(self, state: dict) -> None:
+        for b, st in zip(self._ddp._buckets, state["buckets"]):
+            b.master.copy_(st["master"]); b.s1.copy_(st["s1"]); b.s2.copy_(st["s2"])
+            b.hyper[24:28].copy_(torch.tensor([st["step"]], dtype=torch.int32).view(torch.uint8))
 
 
 def wrap_model(model: nn.Module, device, ddp_kwargs: Optional[dict] = None, comm: Optional[Communicator] = None):
