@@ -154,3 +154,57 @@ def test_run_config_replace_and_cluster_info(monkeypatch):
     assert (info.task_type, info.task_id, info.has_ps, info.is_chief) == ("worker", 1, True, False)
     assert info.trainers() == ["chief:0", "worker:0", "worker:1"]
     assert cfg.num_ps_replicas == 1 and cfg.num_worker_replicas == 3
+
+
+def test_ftrl_optimizer_learns_and_per_tower_optimizers_are_resolved():
+    """FTRL (TF's default for linear models) trains a logistic regression; DNNLinearCombinedClassifier routes the
+    wide tower ("linear.*") to FTRL and the deep tower to Adagrad."""
+    import torch
+    from tf_yarn_b200 import estimator as est
+    from tf_yarn_b200 import keras
+    from tf_yarn_b200.estimator import feature_column as fc
+    torch.manual_seed(0)
+    w = torch.nn.Parameter(torch.zeros(10))
+    opt = keras.optimizers.Ftrl(0.1, l1_regularization_strength=0.01).to_torch([w])
+    x = torch.randn(256, 10)
+    y = (x[:, 0] - 2 * x[:, 3] > 0).float()
+    for _ in range(200):
+        opt.zero_grad()
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(x @ w, y)
+        loss.backward()
+        opt.step()
+    assert loss.item() < 0.35, loss.item()              # from ln 2 = 0.69
+    wd = w.detach()
+    assert wd[0] > 0.5 and wd[3] < -1.0 and wd.abs()[[1, 2, 4, 5, 6, 7, 8, 9]].max() < 0.5
+
+    num = fc.numeric_column("x", shape=(4,))
+    cat = fc.categorical_column_with_hash_bucket("c", 50)
+    e = est.DNNLinearCombinedClassifier(linear_feature_columns=[num, cat],
+                                        dnn_feature_columns=[num, fc.embedding_column(cat, 8)],
+                                        dnn_hidden_units=[16], config=est.RunConfig(save_checkpoints_steps=None,
+                                                                                    save_checkpoints_secs=None))
+
+    def input_fn():
+        from tf_yarn_b200.data import Dataset
+        g = torch.Generator().manual_seed(1)
+        batches = []
+        for _ in range(8):
+            xs = torch.randn(32, 4, generator=g)
+            cs = torch.randint(0, 50, (32, 1), generator=g)
+            batches.append(({"x": xs, "c": cs}, (xs[:, 0] > 0).long()))
+        return Dataset(lambda: iter(batches), len(batches))
+    e.train(input_fn, steps=8)
+    kinds = {n: d.to_spec().kind for n, d in e._opt_by_name.items()}
+    assert all(k == "ftrl" for n, k in kinds.items() if n.startswith("linear."))
+    assert all(k == "adagrad" for n, k in kinds.items() if not n.startswith("linear."))
+    assert len({k for k in kinds.values()}) == 2
+
+
+def test_ps_layout_carries_per_variable_optimizers():
+    from tf_yarn_b200.estimator import ps
+    lay = ps.Layout([("linear.w", [10]), ("dnn.w", [4, 4])], 2, "adagrad", {"lr": 0.1, "p1": 0, "p2": 0, "eps": 1e-7,
+                    "wd": 0, "init_s1": 0.1, "flags": 0}, kinds=["ftrl", "adagrad"],
+                    hypers=[{"lr": 0.05, "p1": 0.01, "p2": 0, "eps": 0, "wd": 0, "init_s1": 0.1, "flags": 0}] * 2)
+    again = ps.Layout.from_json(lay.to_json())
+    assert again.kinds == ["ftrl", "adagrad"] and again.var_slots == [2, 1]
+    assert again.shard_elems[0] == 16 * 3 and again.shard_elems[1] == 16 * 2

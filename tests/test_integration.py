@@ -163,7 +163,9 @@ def test_parameter_server_strategy_end_to_end(tmp_path):
     assert metrics.container_duration[ContainerKey("ps", 1)] is not None
     sc = summary.read_scalars(os.path.join(model_dir, "eval"))
     acc = [v for n, v in zip(sc["name"], sc["value"]) if n == "accuracy"]
-    assert acc[-1] > max(0.8, acc[0])
+    # the first evaluated checkpoint may already be a late one (asynchronous evaluator): require a trained model,
+    # not a strict improvement between two evaluations
+    assert acc[-1] > 0.8 and acc[-1] >= acc[0] - 0.02, acc
     assert max(sc["step"]) >= 200
 
 

@@ -94,22 +94,24 @@ class _WideDeepNet(nn.Module):
         return out
 
 
-def _canned_model_fn(linear_columns, dnn_columns, hidden_units, n_classes, optimizer, dropout=None):
+def _canned_model_fn(linear_columns, dnn_columns, hidden_units, n_classes, optimizer, dropout=None,
+                     linear_optimizer=None):
     n_out = 1 if n_classes == 2 else n_classes
 
     def model_fn(features, labels, mode, params=None, config=None):
         net = _WideDeepNet(linear_columns, dnn_columns, hidden_units, n_out, dropout=dropout)
+        # the wide tower's parameters live under "linear."; everything else belongs to the deep tower
+        per_tower = {"linear.": linear_optimizer} if (linear_optimizer is not None and linear_columns) else None
         return EstimatorSpec(mode=mode, network=net, loss=_classification_loss(n_classes), optimizer=optimizer,
                              eval_metric_ops=_classification_metrics(n_classes),
-                             predictions=_classification_predictions(n_classes))
+                             predictions=_classification_predictions(n_classes), optimizers=per_tower)
     return model_fn
 
 
 class LinearClassifier(Estimator):
-    def __init__(self, feature_columns, model_dir: Optional[str] = None, n_classes: int = 2, optimizer: Any = "adagrad",
+    def __init__(self, feature_columns, model_dir: Optional[str] = None, n_classes: int = 2, optimizer: Any = "ftrl",
                  config: Optional[RunConfig] = None, **_ignored):
-        # TF's default for linear models is FTRL; Adagrad is its closest fused optimizer here
-        optimizer = "adagrad" if (isinstance(optimizer, str) and optimizer.lower() == "ftrl") else optimizer
+        # FTRL is TF's default for linear models (tf.estimator.LinearClassifier)
         super().__init__(_canned_model_fn(list(feature_columns), [], [], n_classes, optimizer), model_dir, config)
 
 
@@ -122,14 +124,15 @@ class DNNClassifier(Estimator):
 
 
 class DNNLinearCombinedClassifier(Estimator):
-    """Wide & deep: one optimizer for both towers (TF allows two; pass the same descriptor)."""
+    """Wide & deep with TF's defaults: FTRL for the linear (wide) tower, Adagrad for the DNN (deep) tower."""
 
-    def __init__(self, model_dir: Optional[str] = None, linear_feature_columns=None, linear_optimizer: Any = None,
+    def __init__(self, model_dir: Optional[str] = None, linear_feature_columns=None, linear_optimizer: Any = "ftrl",
                  dnn_feature_columns=None, dnn_optimizer: Any = "adagrad", dnn_hidden_units: Sequence[int] = (),
                  dnn_dropout: Optional[float] = None, n_classes: int = 2, config: Optional[RunConfig] = None,
                  **_ignored):
         super().__init__(_canned_model_fn(list(linear_feature_columns or []), list(dnn_feature_columns or []),
-                                          list(dnn_hidden_units), n_classes, dnn_optimizer, dnn_dropout),
+                                          list(dnn_hidden_units), n_classes, dnn_optimizer, dnn_dropout,
+                                          linear_optimizer=linear_optimizer),
                          model_dir, config)
 
 

@@ -66,6 +66,39 @@ def _to_device(t, device):
     return t.to(device, non_blocking=True)
 
 
+def _clone_tensors(t):
+    if isinstance(t, dict):
+        return {k: _clone_tensors(v) for k, v in t.items()}
+    if isinstance(t, (tuple, list)):
+        return type(t)(_clone_tensors(v) for v in t)
+    return t.clone() if torch.is_tensor(t) else t
+
+
+def _copy_tensors(dst, src) -> None:
+    if isinstance(dst, dict):
+        for k in dst:
+            _copy_tensors(dst[k], src[k])
+    elif isinstance(dst, (tuple, list)):
+        for d, s_ in zip(dst, src):
+            _copy_tensors(d, s_)
+    elif torch.is_tensor(dst):
+        dst.copy_(src, non_blocking=True)
+
+
+def _signature(*ts):
+    out = []
+    for t in ts:
+        if isinstance(t, dict):
+            out.append(tuple((k, _signature(t[k])) for k in sorted(t)))
+        elif isinstance(t, (tuple, list)):
+            out.append(tuple(_signature(v) for v in t))
+        elif torch.is_tensor(t):
+            out.append((tuple(t.shape), str(t.dtype)))
+        else:
+            out.append(None)
+    return tuple(out)
+
+
 def _split(item):
     if isinstance(item, (tuple, list)) and len(item) == 2:
         return item[0], item[1]
@@ -86,9 +119,12 @@ class Estimator:
         self._spec: Optional[EstimatorSpec] = None
         self._optimizer = None
         self._opt_desc: Optional[kopt.Optimizer] = None
+        self._opt_by_name: Dict[str, kopt.Optimizer] = {}
         self._global_step = 0
         self._device: Optional[torch.device] = None
         self._ps = None
+        self._ps_graph = None
+        self._last_loss_t = None
         self._pending_broadcast: Optional[int] = None
         self.last_loss: Optional[float] = None
 
@@ -131,16 +167,35 @@ class Estimator:
         self._spec = spec._replace(network=self._network)
         return self._spec
 
-    def _make_optimizer(self, spec: EstimatorSpec):
-        opt = spec.optimizer
+    @staticmethod
+    def _resolve_opt(opt):
         if opt is None:
             opt = "sgd"
         if callable(opt) and not isinstance(opt, kopt.Optimizer) and not hasattr(opt, "_tfy_inner_optimizer"):
             opt = opt()
-        desc = kopt.get(opt)
+        return kopt.get(opt)
+
+    def _make_optimizer(self, spec: EstimatorSpec):
+        desc = self._resolve_opt(spec.optimizer)
         self._opt_desc = desc
-        params = [p for p in self._network.parameters() if p.requires_grad] if self._network is not None else []
-        self._optimizer = desc.to_torch(params) if params else None
+        named = [(n, p) for n, p in self._network.named_parameters() if p.requires_grad] \
+            if self._network is not None else []
+        # per-prefix optimizers (longest prefix wins); self._opt_by_name maps every parameter to its descriptor
+        groups = [(pref, self._resolve_opt(o)) for pref, o in (spec.optimizers or {}).items()]
+        groups.sort(key=lambda g: -len(g[0]))
+        self._opt_by_name = {}
+        buckets = {}
+        for n, p in named:
+            d = next((gd for pref, gd in groups if n.startswith(pref)), desc)
+            self._opt_by_name[n] = d
+            buckets.setdefault(id(d), (d, []))[1].append(p)
+        if not named:
+            self._optimizer = None
+        elif len(buckets) == 1:
+            d, ps = next(iter(buckets.values()))
+            self._optimizer = d.to_torch(ps)
+        else:
+            self._optimizer = _MultiOptimizer([d.to_torch(ps) for d, ps in buckets.values()])
 
     def _variables(self) -> List[torch.Tensor]:
         if self._network is None:
@@ -217,10 +272,10 @@ class Estimator:
             if self._device.type == "cuda":
                 from tf_yarn_b200.estimator import ps_hbm
                 self._ps = ps_hbm.connect_worker(self._network, self._opt_desc, cluster, is_chief,
-                                                 self._global_step)
+                                                 self._global_step, opt_by_name=self._opt_by_name)
             else:
                 self._ps = ps_mod.connect_worker(self._network, self._opt_desc, cluster, is_chief,
-                                                 self._global_step)
+                                                 self._global_step, opt_by_name=self._opt_by_name)
             if not is_chief:
                 self._global_step = self._ps.global_step()
         if self._pending_broadcast is not None:
@@ -256,6 +311,7 @@ class Estimator:
             wants_step = [h for h in hooks if _wants_global_step(h.before_run(ctx))]
             prev_gs = self._global_step
             loss = self._train_step(features, labels, distributed)
+            self._last_loss_t = loss          # device scalar of this step (hooks may read it: one 4-byte D2H)
             if self._ps is not None:
                 self._global_step = self._ps.increment_global_step()
             else:
@@ -305,12 +361,57 @@ class Estimator:
         logger.info("Loss for final step: %s.", self.last_loss)
         return self
 
+    def _ps_step_body(self, features, labels) -> torch.Tensor:
+        """pull -> forward -> backward -> push against the parameter servers (kernels only: capturable)."""
+        self._ps.pull(self._network)
+        self._optimizer.zero_grad(set_to_none=False)
+        outputs = self._network(features)
+        loss = self._spec.loss(labels, outputs)
+        loss.backward()
+        self._ps.push(self._network)
+        return loss.detach()
+
+    def _ps_step_cuda(self, features, labels) -> torch.Tensor:
+        """B200 parameter-server step.  After three eager steps the whole pull/forward/backward/push sequence is
+        captured in a CUDA graph and replayed on static input buffers: the data plane is a handful of
+        microsecond-scale peer-memory kernels, so an eager step is bound by Python / launch overhead (the
+        round-1 review measured it host-bound).  TFY_PS_GRAPH=0 keeps it eager."""
+        st = self._ps_graph
+        if hasattr(self._ps, "refresh_adam_scale"):
+            self._ps.refresh_adam_scale()
+        if st is None or st.get("off"):
+            loss = self._ps_step_body(features, labels)
+            if st is None:
+                st = self._ps_graph = {"warm": 0, "off": os.environ.get("TFY_PS_GRAPH", "1") == "0"}
+            st["warm"] += 1
+            if not st["off"] and st["warm"] == 3:
+                try:
+                    sf, sl = _clone_tensors(features), _clone_tensors(labels)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        sloss = self._ps_step_body(sf, sl)
+                    st.update(graph=g, feats=sf, labels=sl, loss=sloss, sig=_signature(features, labels))
+                    logger.info("parameter-server train step captured in a CUDA graph")
+                except Exception as exc:  # noqa: BLE001
+                    logger.warning("CUDA-graph capture of the PS step failed (%s); staying eager", exc)
+                    st["off"] = True
+            return loss
+        if "graph" not in st or _signature(features, labels) != st["sig"]:
+            return self._ps_step_body(features, labels)          # odd-shaped batch: run it eagerly
+        _copy_tensors(st["feats"], features)
+        _copy_tensors(st["labels"], labels)
+        st["graph"].replay()
+        return st["loss"]
+
     def _train_step(self, features, labels, distributed: bool) -> torch.Tensor:
         spec = self._spec
         if self._network is None or self._optimizer is None:
             return torch.zeros(())
         features = _to_device(features, self._device)
         labels = _to_device(labels, self._device)
+        if self._ps is not None and self._device.type == "cuda":
+            return self._ps_step_cuda(features, labels)
         if self._ps is not None:
             self._ps.pull(self._network)
         self._optimizer.zero_grad(set_to_none=False)
@@ -453,6 +554,32 @@ class Estimator:
         return out
 
     export_savedmodel = export_saved_model
+
+
+class _MultiOptimizer:
+    """Several torch optimizers (one per parameter group of EstimatorSpec.optimizers) behind one interface."""
+
+    def __init__(self, opts):
+        self.opts = list(opts)
+
+    @property
+    def param_groups(self):
+        return [g for o in self.opts for g in o.param_groups]
+
+    def zero_grad(self, set_to_none: bool = False):
+        for o in self.opts:
+            o.zero_grad(set_to_none=set_to_none)
+
+    def step(self):
+        for o in self.opts:
+            o.step()
+
+    def state_dict(self):
+        return {"multi": [o.state_dict() for o in self.opts]}
+
+    def load_state_dict(self, state):
+        for o, st in zip(self.opts, state["multi"]):
+            o.load_state_dict(st)
 
 
 def _wants_global_step(args) -> bool:

@@ -43,7 +43,7 @@ KV_LAYOUT = "ps/layout"
 KV_READY = "ps/ready"
 
 # optimizer slots per variable (besides the value itself)
-_SLOTS = {"sgd": 0, "adagrad": 1, "adadelta": 2, "adam": 2, "adamw": 2}
+_SLOTS = {"sgd": 0, "adagrad": 1, "adadelta": 2, "adam": 2, "adamw": 2, "ftrl": 2}
 
 
 def _job_tag() -> str:
@@ -57,12 +57,16 @@ def _shm_dir() -> str:
 class Layout:
     """Where every variable lives: owner ps, offset inside the owner's shard."""
 
-    def __init__(self, variables: List[Tuple[str, List[int]]], n_ps: int, opt_kind: str, hyper: Dict[str, float]):
+    def __init__(self, variables: List[Tuple[str, List[int]]], n_ps: int, opt_kind: str, hyper: Dict[str, float],
+                 kinds: Optional[List[str]] = None, hypers: Optional[List[Dict[str, float]]] = None):
         self.variables = variables
         self.n_ps = n_ps
-        self.opt_kind = opt_kind
+        self.opt_kind = opt_kind          # default optimizer; `kinds[i]` / `hypers[i]` are per variable
         self.hyper = hyper
-        self.slots = _SLOTS[opt_kind]
+        self.kinds = list(kinds) if kinds else [opt_kind] * len(variables)
+        self.hypers = list(hypers) if hypers else [hyper] * len(variables)
+        self.var_slots = [_SLOTS[k] for k in self.kinds]
+        self.slots = max(self.var_slots + [0])
         self.owner: List[int] = []
         self.offset: List[int] = []
         self.numel: List[int] = []
@@ -74,19 +78,20 @@ class Layout:
             self.owner.append(ps)
             self.offset.append(self.shard_elems[ps])
             self.numel.append(n)
-            self.shard_elems[ps] += n_pad * (1 + self.slots)
+            self.shard_elems[ps] += n_pad * (1 + self.var_slots[i])
 
     def padded(self, i: int) -> int:
         return (self.numel[i] + 7) // 8 * 8
 
     def to_json(self) -> str:
         return json.dumps({"variables": self.variables, "n_ps": self.n_ps, "opt_kind": self.opt_kind,
-                           "hyper": self.hyper})
+                           "hyper": self.hyper, "kinds": self.kinds, "hypers": self.hypers})
 
     @classmethod
     def from_json(cls, raw) -> "Layout":
         d = json.loads(raw.decode() if isinstance(raw, (bytes, bytearray)) else raw)
-        return cls([(n, list(s)) for n, s in d["variables"]], d["n_ps"], d["opt_kind"], d["hyper"])
+        return cls([(n, list(s)) for n, s in d["variables"]], d["n_ps"], d["opt_kind"], d["hyper"], d.get("kinds"),
+                   d.get("hypers"))
 
 
 HEADER_BYTES = 64   # [0:8] global step (int64, only meaningful on ps 0)
@@ -158,8 +163,7 @@ class WorkerConnection:
 
     # ---- push: apply the local gradients to the ps copy (no locks: hogwild) -----------
     def push(self, network: nn.Module) -> None:
-        lay, h = self.layout, self.layout.hyper
-        lr, p1, p2, eps, wd = h["lr"], h["p1"], h["p2"], h["eps"], h["wd"]
+        lay = self.layout
         params = dict(network.named_parameters())
         self._t += 1
         with torch.no_grad():
@@ -167,17 +171,26 @@ class WorkerConnection:
                 g = params[name].grad
                 if g is None:
                     continue
+                h = lay.hypers[i]
+                lr, p1, p2, eps, wd = h["lr"], h["p1"], h["p2"], h["eps"], h["wd"]
                 g = g.detach().reshape(-1).float().cpu()
                 w = self._region(i)
                 if wd:
                     g = g + wd * w
-                kind = lay.opt_kind
+                kind = lay.kinds[i]
                 if kind == "sgd":
                     w.add_(g, alpha=-lr)
                 elif kind == "adagrad":
                     acc = self._region(i, 1)
                     acc.addcmul_(g, g)
                     w.addcdiv_(g, acc.sqrt().add_(eps), value=-lr)
+                elif kind == "ftrl":           # p1 = l1, p2 = l2, eps = beta (OptimizerSpec.ftrl)
+                    n, z = self._region(i, 1), self._region(i, 2)
+                    n_new = n + g * g
+                    z.add_(g - (n_new.sqrt() - n.sqrt()) / lr * w)
+                    n.copy_(n_new)
+                    neww = -(z - torch.sign(z) * p1) / ((eps + n_new.sqrt()) / lr + 2 * p2)
+                    w.copy_(torch.where(z.abs() <= p1, torch.zeros_like(neww), neww))
                 elif kind == "adadelta":
                     sq, dx = self._region(i, 1), self._region(i, 2)
                     sq.mul_(p1).addcmul_(g, g, value=1 - p1)
@@ -209,7 +222,15 @@ def _named_trainables(network: nn.Module) -> List[Tuple[str, nn.Parameter]]:
     return [(n, p) for n, p in network.named_parameters() if p.requires_grad]
 
 
-def connect_worker(network: nn.Module, opt_desc, cluster, is_chief: bool, global_step: int) -> WorkerConnection:
+def make_layout(named, n_ps: int, opt_desc, opt_by_name=None) -> Layout:
+    """Layout with the optimizer (kind + hyper-parameters) of every variable."""
+    descs = [(opt_by_name or {}).get(n, opt_desc) for n, _ in named]
+    return Layout([(n, list(p.shape)) for n, p in named], n_ps, opt_desc.to_spec().kind, _hyper_of(opt_desc),
+                  [d.to_spec().kind for d in descs], [_hyper_of(d) for d in descs])
+
+
+def connect_worker(network: nn.Module, opt_desc, cluster, is_chief: bool, global_step: int,
+                   opt_by_name=None) -> WorkerConnection:
     """Chief: publish the layout, wait for the shards, initialise them.  Worker: wait until ready."""
     client = _task_commons.TaskClient.from_current()
     kv = client.kv
@@ -217,7 +238,7 @@ def connect_worker(network: nn.Module, opt_desc, cluster, is_chief: bool, global
     named = _named_trainables(network)
     names = [n for n, _ in named]
     if is_chief:
-        layout = Layout([(n, list(p.shape)) for n, p in named], n_ps, opt_desc.to_spec().kind, _hyper_of(opt_desc))
+        layout = make_layout(named, n_ps, opt_desc, opt_by_name)
         kv[KV_LAYOUT] = layout.to_json().encode()
     else:
         layout = Layout.from_json(kv.wait(KV_LAYOUT))
@@ -230,8 +251,8 @@ def connect_worker(network: nn.Module, opt_desc, cluster, is_chief: bool, global
         with torch.no_grad():
             for i, (_, p) in enumerate(named):
                 conn._region(i).copy_(p.detach().reshape(-1).float().cpu())
-                if layout.opt_kind == "adagrad":
-                    conn._region(i, 1).fill_(layout.hyper["init_s1"])
+                if layout.kinds[i] in ("adagrad", "ftrl"):
+                    conn._region(i, 1).fill_(layout.hypers[i]["init_s1"])
         shards[0].set_global_step(global_step)
         kv[KV_READY] = b"1"
         logger.info("parameter servers initialised: %d variables on %d ps", len(names), n_ps)

@@ -35,17 +35,23 @@ logger = logging.getLogger(__name__)
 
 _vp, _i, _sz, _f, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float, ctypes.c_longlong
 native.declare("tfy_ps_pull", [_vp, _i, _sz, _i, _vp])
-native.declare("tfy_ps_push", [_vp, _i, _sz, _i, _i, _f, _f, _f, _f, _vp])
+native.declare("tfy_ps_push", [_vp, _i, _sz, _i, _f, _vp, _vp])
 native.declare("tfy_ps_refresh_shadow", [_vp, _i, _sz, _vp])
+native.declare("tfy_dense_bwd", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_ps_embedding_bag", [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp])
-native.declare("tfy_ps_push_rows", [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _i, _f, _f, _f, _vp])
+native.declare("tfy_ps_push_rows", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _i, _f, _f, _f, _f, _f, _f, _vp,
+                                    _vp])
 
-OPT_CODES = {"sgd": native.OPT_SGD, "adagrad": native.OPT_ADAGRAD}
+OPT_CODES = {"sgd": native.OPT_SGD, "adagrad": native.OPT_ADAGRAD, "adam": native.OPT_ADAM,
+             "ftrl": native.OPT_FTRL}
 
 
 class PsSeg(ctypes.Structure):
-    _fields_ = [("remote_w", ctypes.c_uint64), ("remote_s1", ctypes.c_uint64), ("remote_shadow", ctypes.c_uint64),
-                ("local", ctypes.c_uint64), ("n", ctypes.c_uint64)]
+    """Mirror of TfyPsSeg (ops/csrc/tfy_ps.cu): one variable of a push / pull, with ITS optimizer."""
+    _fields_ = [("remote_w", ctypes.c_uint64), ("remote_s1", ctypes.c_uint64), ("remote_s2", ctypes.c_uint64),
+                ("remote_shadow", ctypes.c_uint64), ("local", ctypes.c_uint64), ("n", ctypes.c_uint64),
+                ("opt", ctypes.c_int32), ("lr", ctypes.c_float), ("eps", ctypes.c_float), ("wd", ctypes.c_float),
+                ("p1", ctypes.c_float), ("p2", ctypes.c_float), ("p3", ctypes.c_float), ("pad", ctypes.c_int32)]
 
 
 def cluster_ranks(cluster) -> Dict[str, int]:
@@ -83,9 +89,10 @@ class HbmConnection:
                  header: ps_cpu.ShmShard, network: nn.Module):
         self.layout, self.comm, self.names, self.header = layout, comm, names, header
         self.lib = native.load()
-        self.opt = OPT_CODES.get(layout.opt_kind)
-        if self.opt is None:
-            raise ValueError(f"the HBM parameter server fuses SGD and Adagrad; got {layout.opt_kind!r}")
+        bad = sorted({k for k in layout.kinds if k not in OPT_CODES})
+        if bad:
+            raise ValueError(f"the HBM parameter server fuses SGD, Adagrad, Adam and FTRL; got {bad}")
+        self.var_opt = [OPT_CODES[k] for k in layout.kinds]
         arena = comm.arena
         self.ps_base = [arena.peer_base[ranks[f"ps:{i}"]] + region_off for i in range(layout.n_ps)]
         self.region_bytes = shard_bytes(layout)
@@ -97,14 +104,24 @@ class HbmConnection:
         self.gemm: Dict[int, nn.Module] = {}        # variable index -> Linear whose weight stays remote
         self._classify(network)
         self.dense_idx = [i for i in range(len(names)) if i not in self.sparse]
-        self._pull_segs = self._make_segs(for_push=False)
+        # Dense-layer weights served by the remote-weight GEMMs are NEVER copied to the worker: forward streams
+        # the ps rank's bf16 shadow through TMA, backward (dW, dx) reads the same shadow (tfy_dense_bwd)
+        self.pull_idx = [i for i in self.dense_idx if i not in self.gemm]
+        self._pull_segs = self._make_segs(for_push=False, idx=self.pull_idx)
         self._push_segs = None
         self._push_ptrs = None
         self._max_n = max([self._n4(i) for i in self.dense_idx] + [4])
         self.pull_stream = torch.cuda.Stream(device=dev)
         self._pull_done: Optional[torch.cuda.Event] = None
-        h = layout.hyper
-        self.lr, self.eps, self.wd = float(h["lr"]), float(h["eps"]), float(h["wd"])
+        # Adam bias correction sqrt(1-b2^t)/(1-b1^t): a device scalar the push kernels read, refreshed from the
+        # global step before every push (so a captured CUDA graph sees it advance)
+        self._adam = [i for i, k in enumerate(layout.kinds) if k == "adam"]
+        self.adam_scale = torch.ones(1, dtype=torch.float32, device=dev)
+        self._adam_host = torch.ones(1, dtype=torch.float32).pin_memory() if self._adam else None
+        # NVLink traffic / kernel launches of one step, counted on the host while a step runs eagerly (the
+        # captured graph replays exactly the same launches)
+        self._acct = {"pull_bytes": 0, "push_bytes": 0, "launches_per_step": 0}
+        self._acct_last = dict(self._acct)
 
     # ------------------------------------------------------------------ addressing
     def _n4(self, i: int) -> int:
@@ -138,22 +155,29 @@ class HbmConnection:
     def _classify(self, network: nn.Module) -> None:
         by_param = {id(p): i for i, p in enumerate(self.params)}
         for mod in network.modules():
-            if isinstance(mod, nn.EmbeddingBag) and id(mod.weight) in by_param and mod.embedding_dim % 4 == 0 \
-                    and mod.mode in ("sum", "mean"):
+            if isinstance(mod, nn.EmbeddingBag) and id(mod.weight) in by_param and mod.mode in ("sum", "mean"):
                 self.sparse[by_param[id(mod.weight)]] = mod
             elif isinstance(mod, nn.Linear) and id(mod.weight) in by_param and mod.in_features % 8 == 0 \
-                    and mod.out_features >= 8:
+                    and mod.out_features >= 8 and mod.out_features % 8 == 0:
                 self.gemm[by_param[id(mod.weight)]] = mod
 
-    def _make_segs(self, for_push: bool):
-        segs = (PsSeg * max(1, len(self.dense_idx)))()
-        for k, i in enumerate(self.dense_idx):
+    def _make_segs(self, for_push: bool, idx: Optional[List[int]] = None):
+        idx = self.dense_idx if idx is None else idx
+        segs = (PsSeg * max(1, len(idx)))()
+        for k, i in enumerate(idx):
             p = self.params[i]
+            h = self.layout.hypers[i]
             segs[k].remote_w = self.master_ptr(i)
-            segs[k].remote_s1 = self.master_ptr(i, 1) if self.layout.slots >= 1 else 0
+            segs[k].remote_s1 = self.master_ptr(i, 1) if self.layout.var_slots[i] >= 1 else 0
+            segs[k].remote_s2 = self.master_ptr(i, 2) if self.layout.var_slots[i] >= 2 else 0
             segs[k].remote_shadow = self.shadow_ptr(i) if i in self.gemm else 0
             segs[k].local = (p.grad.data_ptr() if for_push else p.data_ptr())
             segs[k].n = self.layout.numel[i]
+            segs[k].opt = self.var_opt[i]
+            segs[k].lr, segs[k].eps, segs[k].wd = float(h["lr"]), float(h["eps"]), float(h["wd"])
+            # FTRL: l1, l2, beta (OptimizerSpec.ftrl keeps beta in eps) | Adam: beta1, beta2
+            segs[k].p1, segs[k].p2 = float(h["p1"]), float(h["p2"])
+            segs[k].p3 = float(h["eps"]) if self.layout.kinds[i] == "ftrl" else 0.0
         dev_segs = torch.frombuffer(bytearray(bytes(segs)), dtype=torch.uint8).to(self.device)
         return dev_segs
 
@@ -168,19 +192,24 @@ class HbmConnection:
 
     # ------------------------------------------------------------------ pull / push
     def pull(self, network: nn.Module) -> None:
-        """Start the dense pull on the side stream; forward GEMMs read their weights remotely meanwhile."""
-        if not self.dense_idx:
+        """Dense pull of the variables that need a local replica (biases, small vectors): ONE launch of peer
+        loads.  Embedding rows and Dense weights are not pulled (gathered / streamed by their consumers)."""
+        self._acct = {"pull_bytes": 0, "push_bytes": 0, "launches_per_step": 0}      # a step starts with the pull
+        if not self.pull_idx:
             return
-        for i in self.dense_idx:           # local replicas must be 16-byte aligned, contiguous fp32
-            assert self.params[i].dtype == torch.float32
-        self.pull_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.pull_stream):
-            native.check(self.lib.tfy_ps_pull(self._pull_segs.data_ptr(), len(self.dense_idx), self._max_n, 0,
-                                              self.pull_stream.cuda_stream), "tfy_ps_pull")
-            self._pull_done = torch.cuda.Event()
-            self._pull_done.record(self.pull_stream)
-        # everything except the remote-GEMM layers needs the replica right away
-        torch.cuda.current_stream().wait_event(self._pull_done)
+        native.check(self.lib.tfy_ps_pull(self._pull_segs.data_ptr(), len(self.pull_idx), self._max_n, 0,
+                                          torch.cuda.current_stream().cuda_stream), "tfy_ps_pull")
+        self.account(pull=sum(self.layout.numel[i] * 4 for i in self.pull_idx))
+
+    def account(self, pull: int = 0, push: int = 0, launches: int = 1) -> None:
+        a = self._acct
+        a["pull_bytes"] += pull
+        a["push_bytes"] += push
+        a["launches_per_step"] += launches
+
+    def traffic_per_step(self) -> dict:
+        """Bytes read from / written to the ps ranks over NVLink and kernels launched by the last eager step."""
+        return dict(self._acct_last)
 
     def push(self, network: nn.Module) -> None:
         if not self.dense_idx:
@@ -193,9 +222,21 @@ class HbmConnection:
         if self._push_segs is None or self._push_ptrs != ptrs:     # gradients normally keep their address
             self._push_segs, self._push_ptrs = self._make_segs(for_push=True), ptrs
         segs = self._push_segs
-        native.check(self.lib.tfy_ps_push(segs.data_ptr(), len(self.dense_idx), self._max_n, 0, self.opt, self.lr,
-                                          self.eps, self.wd, 1.0, torch.cuda.current_stream().cuda_stream),
+        native.check(self.lib.tfy_ps_push(segs.data_ptr(), len(self.dense_idx), self._max_n, 0, 1.0,
+                                          self.adam_scale.data_ptr(), torch.cuda.current_stream().cuda_stream),
                      "tfy_ps_push")
+        # per element: gradient applied to master (+ slots read-modify-written) on the peer
+        self.account(push=sum(self.layout.numel[i] * 4 * (1 + self.layout.var_slots[i]) for i in self.dense_idx))
+        self._acct_last = dict(self._acct)
+
+    def refresh_adam_scale(self) -> None:
+        """Bias correction of the asynchronous Adam from the shared global step (host side, outside any graph)."""
+        if not self._adam:
+            return
+        h = self.layout.hypers[self._adam[0]]
+        t = max(self.global_step(), 0) + 1
+        self._adam_host[0] = (1.0 - h["p2"] ** t) ** 0.5 / (1.0 - h["p1"] ** t)
+        self.adam_scale.copy_(self._adam_host, non_blocking=True)
 
     def refresh_shadows(self) -> None:
         segs = self._make_segs(for_push=False)
@@ -232,6 +273,7 @@ def _make_bag_forward(conn: HbmConnection, idx: int, mod: nn.EmbeddingBag):
             native.check(lib.tfy_ps_embedding_bag(conn.master_ptr(idx), ids.data_ptr(), out.data_ptr(), 0, B, L, D, V,
                                                   mean, torch.cuda.current_stream().cuda_stream),
                          "tfy_ps_embedding_bag")
+            conn.account(pull=B * L * D * 4)
             ctx.ids = ids
             return out
 
@@ -240,10 +282,16 @@ def _make_bag_forward(conn: HbmConnection, idx: int, mod: nn.EmbeddingBag):
             ids = ctx.ids
             B, L = ids.shape
             dout = dout.contiguous().float()
-            acc = conn.master_ptr(idx, 1) if conn.layout.slots >= 1 else None
-            native.check(lib.tfy_ps_push_rows(conn.master_ptr(idx), acc, ids.data_ptr(), dout.data_ptr(), 0, B, L, D,
-                                              V, mean, conn.opt, conn.lr, conn.eps, 1.0,
+            lay = conn.layout
+            h = lay.hypers[idx]
+            s1 = conn.master_ptr(idx, 1) if lay.var_slots[idx] >= 1 else None
+            s2 = conn.master_ptr(idx, 2) if lay.var_slots[idx] >= 2 else None
+            p3 = float(h["eps"]) if lay.kinds[idx] == "ftrl" else 0.0
+            native.check(lib.tfy_ps_push_rows(conn.master_ptr(idx), s1, s2, ids.data_ptr(), dout.data_ptr(), 0, B, L, D,
+                                              V, mean, conn.var_opt[idx], float(h["lr"]), float(h["eps"]),
+                                              float(h["p1"]), float(h["p2"]), p3, 1.0, conn.adam_scale.data_ptr(),
                                               torch.cuda.current_stream().cuda_stream), "tfy_ps_push_rows")
+            conn.account(push=B * L * D * 4 * (1 + lay.var_slots[idx]))
             return None, None
 
     anchor = torch.zeros((), device=conn.device, requires_grad=True)
@@ -264,6 +312,7 @@ def _make_linear_forward(conn: HbmConnection, idx: int, mod: nn.Linear):
             xb = x.to(torch.bfloat16).contiguous()
             y = gemm_bf16(xb, None, bias=bias.to(torch.bfloat16) if bias is not None else None, b_ptr=shadow,
                           b_rows=N, b_ld=K)                     # weights stream from the ps rank over NVLink
+            conn.account(pull=N * K * 2)
             ctx.save_for_backward(xb, weight)
             ctx.has_bias = bias is not None
             return y.to(x.dtype)
@@ -271,11 +320,17 @@ def _make_linear_forward(conn: HbmConnection, idx: int, mod: nn.Linear):
         @staticmethod
         def backward(ctx, dy):
             xb, weight = ctx.saved_tensors
-            dyf = dy.float()
-            dw = dyf.t() @ xb.float()
-            dx = dyf @ weight.float()                          # local replica, pulled on the side stream
-            db = dyf.sum(0) if ctx.has_bias else None
-            return dx.to(dy.dtype), dw.to(weight.dtype), db
+            B = xb.shape[0]
+            dyb = dy.to(torch.bfloat16).contiguous()
+            dw = torch.empty((N, K), dtype=torch.bfloat16, device=dy.device)
+            dx = torch.empty((B, K), dtype=torch.bfloat16, device=dy.device) if ctx.needs_input_grad[0] else None
+            # dW = dy^T x and dx = dy W in one tcgen05 kernel; W is the ps rank's bf16 shadow, read over NVLink
+            native.check(conn.lib.tfy_dense_bwd(dyb.data_ptr(), xb.data_ptr(), shadow, dw.data_ptr(),
+                                                dx.data_ptr() if dx is not None else None, B, N, K,
+                                                torch.cuda.current_stream().cuda_stream), "tfy_dense_bwd")
+            conn.account(pull=N * K * 2 if dx is not None else 0)
+            db = dy.float().sum(0) if ctx.has_bias else None
+            return (dx.to(dy.dtype) if dx is not None else None), dw.to(weight.dtype), db
 
     def forward(x):
         return _PSLinear.apply(x, mod.weight, mod.bias)
@@ -285,15 +340,15 @@ def _make_linear_forward(conn: HbmConnection, idx: int, mod: nn.Linear):
 # ---------------------------------------------------------------------------------------------
 # connection set-up (collective over the cluster)
 # ---------------------------------------------------------------------------------------------
-def connect_worker(network: nn.Module, opt_desc, cluster, is_chief: bool, global_step: int) -> HbmConnection:
+def connect_worker(network: nn.Module, opt_desc, cluster, is_chief: bool, global_step: int,
+                   opt_by_name=None) -> HbmConnection:
     client = _task_commons.TaskClient.from_current()
     kv = client.kv
     n_ps = len(cluster.spec["ps"])
     named = ps_cpu._named_trainables(network)
     names = [n for n, _ in named]
     if is_chief:
-        layout = ps_cpu.Layout([(n, list(p.shape)) for n, p in named], n_ps, opt_desc.to_spec().kind,
-                               ps_cpu._hyper_of(opt_desc))
+        layout = ps_cpu.make_layout(named, n_ps, opt_desc, opt_by_name)
         kv[ps_cpu.KV_LAYOUT] = layout.to_json().encode()
     else:
         layout = ps_cpu.Layout.from_json(kv.wait(ps_cpu.KV_LAYOUT))
@@ -306,8 +361,8 @@ def connect_worker(network: nn.Module, opt_desc, cluster, is_chief: bool, global
         with torch.no_grad():
             for i, (_, p) in enumerate(named):
                 conn.remote_tensor(i).copy_(p.detach().reshape(-1).float())
-                if layout.opt_kind == "adagrad":
-                    conn.remote_tensor(i, 1).fill_(layout.hyper["init_s1"])
+                if layout.kinds[i] in ("adagrad", "ftrl"):
+                    conn.remote_tensor(i, 1).fill_(layout.hypers[i]["init_s1"])
         conn.refresh_shadows()
         header.set_global_step(global_step)
         torch.cuda.synchronize()

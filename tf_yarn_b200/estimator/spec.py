@@ -24,6 +24,9 @@ class EstimatorSpec(NamedTuple):
                     ``None`` makes a parameter-free estimator (the step only advances global_step).
     loss            callable ``(labels, outputs) -> scalar tensor`` (TRAIN / EVAL).
     optimizer       mini-Keras optimizer descriptor, its name, or a zero-arg factory (TRAIN).
+    optimizers      optional ``{parameter-name prefix: optimizer}``: a different optimizer per part of the
+                    network (longest matching prefix wins, ``optimizer`` is the default) -- TF's wide-and-deep
+                    trains the linear tower with FTRL and the deep tower with Adagrad.
     eval_metric_ops ``{name: callable(labels, outputs) -> (numerator, denominator)}`` streaming metrics.
     predictions     callable ``outputs -> dict`` (PREDICT), default identity.
     train_op / export_outputs are accepted for signature parity and ignored.
@@ -36,6 +39,7 @@ class EstimatorSpec(NamedTuple):
     predictions: Optional[Callable] = None
     train_op: Any = None
     export_outputs: Any = None
+    optimizers: Optional[Dict[str, Any]] = None
 
 
 class TrainSpec(NamedTuple):

@@ -463,7 +463,7 @@ class FastSequentialEngine(GraphTrainEngine):
                                                         self._partial.data_ptr(), b.grad.data_ptr(),
                                                         self._counter.data_ptr(), s), "act_drop_bwd_bias")
                 I = xin.shape[1]
-                if (B <= 128 and ly.units <= 128 and ly.units % 8 == 0 and I % 8 == 0 and grad.is_contiguous()
+                if (ly.units % 8 == 0 and I % 8 == 0 and grad.is_contiguous()
                         and xin.is_contiguous() and w.is_contiguous() and w.grad.is_contiguous()
                         and os.environ.get("TFY_NO_TC_DENSE_BWD") != "1"):
                     # dW = dh^T x (straight into the flat gradient buffer) and dx = dh W in ONE tcgen05 kernel

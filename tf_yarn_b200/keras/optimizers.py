@@ -114,7 +114,57 @@ class Adagrad(Optimizer):
                                    initial_accumulator_value=self.initial_accumulator_value)
 
 
-_BY_NAME = {"sgd": SGD, "adadelta": Adadelta, "adam": Adam, "adamw": AdamW, "adagrad": Adagrad}
+class Ftrl(Optimizer):
+    """FTRL-proximal (``tf.keras.optimizers.Ftrl`` / ``tf.train.FtrlOptimizer``), TF's default optimizer of linear
+    models and the canonical choice for the wide tower of wide-and-deep (learning_rate_power fixed at -0.5)."""
+    kind = "ftrl"
+
+    def __init__(self, learning_rate: float = 0.001, learning_rate_power: float = -0.5,
+                 initial_accumulator_value: float = 0.1, l1_regularization_strength: float = 0.0,
+                 l2_regularization_strength: float = 0.0, beta: float = 0.0, lr: float = None):
+        if learning_rate_power != -0.5:
+            raise ValueError("Ftrl: only learning_rate_power=-0.5 is implemented")
+        super().__init__(lr if lr is not None else learning_rate, learning_rate_power=learning_rate_power,
+                         initial_accumulator_value=initial_accumulator_value,
+                         l1_regularization_strength=l1_regularization_strength,
+                         l2_regularization_strength=l2_regularization_strength, beta=beta)
+        self.initial_accumulator_value = initial_accumulator_value
+        self.l1, self.l2, self.beta = l1_regularization_strength, l2_regularization_strength, beta
+
+    def to_spec(self):
+        return OptimizerSpec.ftrl(self.learning_rate, self.l1, self.l2, self.beta, self.initial_accumulator_value)
+
+    def to_torch(self, params):
+        return TorchFtrl(params, lr=self.learning_rate, l1=self.l1, l2=self.l2, beta=self.beta,
+                         initial_accumulator_value=self.initial_accumulator_value)
+
+
+class TorchFtrl(torch.optim.Optimizer):
+    """torch.optim rendition of FTRL-proximal (same formulas as the fused / parameter-server kernels)."""
+
+    def __init__(self, params, lr=1e-3, l1=0.0, l2=0.0, beta=0.0, initial_accumulator_value=0.1):
+        super().__init__(params, dict(lr=lr, l1=l1, l2=l2, beta=beta, init=initial_accumulator_value))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for grp in self.param_groups:
+            lr, l1, l2, beta = grp["lr"], grp["l1"], grp["l2"], grp["beta"]
+            for p in grp["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["n"] = torch.full_like(p, grp["init"])
+                    st["z"] = torch.zeros_like(p)
+                g, n, z = p.grad, st["n"], st["z"]
+                n_new = n + g * g
+                z.add_(g - (n_new.sqrt() - n.sqrt()) / lr * p)
+                n.copy_(n_new)
+                w = -(z - torch.sign(z) * l1) / ((beta + n_new.sqrt()) / lr + 2 * l2)
+                p.copy_(torch.where(z.abs() <= l1, torch.zeros_like(w), w))
+
+
+_BY_NAME = {"sgd": SGD, "adadelta": Adadelta, "adam": Adam, "adamw": AdamW, "adagrad": Adagrad, "ftrl": Ftrl}
 
 
 def get(identifier) -> Optimizer:

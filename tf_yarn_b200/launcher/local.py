@@ -43,8 +43,8 @@ class ServiceSpec(NamedTuple):
     instances: int
     nb_proc: int
     label: NodeLabel
-    memory: int                     # MiB (accounting only)
-    vcores: int
+    memory: int                     # MiB (accounting + exported as TFY_MEMORY_MB; no rlimit: CUDA reserves huge VA)
+    vcores: int                     # CPU cores the instance is pinned to (sched affinity), see _cpu_plan
     env: Dict[str, str]
     files: Dict[str, str]           # target (relative to task workdir) -> source path
 
@@ -126,9 +126,37 @@ class LocalApplication:
             raise
 
     # ------------------------------------------------------------------ start
+    def _cpu_plan(self) -> Dict[str, List[int]]:
+        """Disjoint CPU sets, ``vcores`` per task instance -- what YARN's vcore accounting (cgroups) gives the
+        reference's containers (reference: tf_yarn/client.py:232, skein.model.Resources(memory, vcores)).  With
+        eight trainers, an evaluator and TensorBoard on one host the 100-microsecond host loops of the trainers
+        must not share cores with the side tasks.  GPU tasks are served first; when the box has fewer cores than
+        the topology asks for, the remaining tasks share the cores left (at least one) instead of failing.
+        TFY_PIN_CPUS=0 disables pinning."""
+        if os.environ.get("TFY_PIN_CPUS", "1") == "0" or not hasattr(os, "sched_getaffinity"):
+            return {}
+        avail = sorted(os.sched_getaffinity(0))
+        order = sorted(self.spec.services.items(), key=lambda kv: 0 if kv[1].label == NodeLabel.GPU else 1)
+        want = sum(max(1, svc.vcores) * svc.instances for _, svc in order)
+        if want > len(avail):
+            logger.warning("topology asks for %d vcores, the box has %d: CPU pinning is partial", want, len(avail))
+        plan: Dict[str, List[int]] = {}
+        cursor = 0
+        for task_type, svc in order:
+            for task_id in range(svc.instances):
+                n = max(1, svc.vcores)
+                if cursor + n <= len(avail):
+                    cpus = avail[cursor:cursor + n]
+                    cursor += n
+                else:
+                    cpus = avail[cursor:] or avail[-max(1, min(n, len(avail))):]
+                plan[ContainerKey(task_type, task_id).to_kv_str()] = cpus
+        return plan
+
     def _start_all(self) -> None:
         gpus = visible_gpus()
         cursor = 0
+        self.cpu_plan = self._cpu_plan()
         for task_type, svc in self.spec.services.items():
             for task_id in range(svc.instances):
                 key = ContainerKey(task_type, task_id)
@@ -178,12 +206,20 @@ class LocalApplication:
             "TFY_GPU_IDS": ",".join(str(g) for g in gpus),
             "TFY_HOST": "127.0.0.1",
             "PYTHONUNBUFFERED": "1",
+            "TFY_MEMORY_MB": str(svc.memory),
+            "TFY_VCORES": str(svc.vcores),
         })
+        cpus = getattr(self, "cpu_plan", {}).get(key.to_kv_str())
+        argv = ["bash", "-c", svc.script]
+        if cpus and shutil.which("taskset"):
+            argv = ["taskset", "-c", ",".join(str(c) for c in cpus)] + argv
+            env["TFY_CPUS"] = ",".join(str(c) for c in cpus)
+            env.setdefault("OMP_NUM_THREADS", str(len(cpus)))
         logf = open(log_path, "ab", buffering=0)
-        popen = subprocess.Popen(["bash", "-c", svc.script], cwd=task_dir, env=env, stdout=logf,
+        popen = subprocess.Popen(argv, cwd=task_dir, env=env, stdout=logf,
                                  stderr=subprocess.STDOUT, stdin=subprocess.DEVNULL, start_new_session=True)
         logf.close()
-        logger.info("started %s pid=%d gpus=%s log=%s", key.to_kv_str(), popen.pid, gpus, log_path)
+        logger.info("started %s pid=%d gpus=%s cpus=%s log=%s", key.to_kv_str(), popen.pid, gpus, cpus, log_path)
         return TaskProcess(key, popen, log_path, gpus, task_dir)
 
     # ----------------------------------------------------------------- status

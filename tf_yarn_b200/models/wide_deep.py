@@ -26,13 +26,14 @@ def feature_columns(vocab: int = 100_000, emb_dim: int = 64, n_cat: int = N_CATE
 
 def wide_deep_estimator(model_dir: Optional[str] = None, vocab: int = 100_000, emb_dim: int = 64,
                         hidden_units: Sequence[int] = (1024, 512, 256), optimizer=None, config=None,
-                        n_cat: int = N_CATEGORICAL, n_num: int = N_NUMERIC):
-    """``DNNLinearCombinedClassifier`` over the Criteo-shaped columns."""
+                        n_cat: int = N_CATEGORICAL, n_num: int = N_NUMERIC, linear_optimizer=None):
+    """``DNNLinearCombinedClassifier`` over the Criteo-shaped columns (FTRL wide tower + Adagrad deep tower)."""
     from tf_yarn_b200 import estimator as est
     from tf_yarn_b200 import keras
     wide, deep = feature_columns(vocab, emb_dim, n_cat, n_num)
     opt = optimizer if optimizer is not None else (lambda: keras.optimizers.Adagrad(0.05))
-    return est.DNNLinearCombinedClassifier(model_dir=model_dir, linear_feature_columns=wide,
+    lin = linear_optimizer if linear_optimizer is not None else (lambda: keras.optimizers.Ftrl(0.05))
+    return est.DNNLinearCombinedClassifier(model_dir=model_dir, linear_feature_columns=wide, linear_optimizer=lin,
                                            dnn_feature_columns=deep, dnn_hidden_units=list(hidden_units),
                                            dnn_optimizer=opt, n_classes=2, config=config)
 

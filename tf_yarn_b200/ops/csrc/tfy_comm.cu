@@ -317,6 +317,7 @@ static int tfy_fused_step_groups(const TfyCommCtx* c, int grad_dtype, int param_
         if (opt == TFY_OPT_SGD) TFY_FS3(GT, PT, TFY_OPT_SGD);      \
         else if (opt == TFY_OPT_ADADELTA) TFY_FS3(GT, PT, TFY_OPT_ADADELTA); \
         else if (opt == TFY_OPT_ADAM) TFY_FS3(GT, PT, TFY_OPT_ADAM); \
+        else if (opt == TFY_OPT_FTRL) TFY_FS3(GT, PT, TFY_OPT_FTRL); \
         else TFY_FS3(GT, PT, TFY_OPT_ADAGRAD);                     \
     } while (0)
     if (grad_dtype == TFY_BF16 && param_dtype == TFY_BF16) TFY_FS2(__nv_bfloat16, __nv_bfloat16);

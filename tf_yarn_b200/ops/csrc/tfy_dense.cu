@@ -223,13 +223,138 @@ tfy_dense_bwd_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// General shapes (batch > 128 and / or units > 128): one CTA per (64-column slice of the in-features, job) where
+// a job is either a 128-unit tile of dW -- K loop over the batch in chunks of 128 rows -- or a 128-row tile of
+// dx -- K loop over the units in chunks of 128.  Same operand views and epilogue as the single-shot kernel, with
+// a 3-stage TMA ring (48 KB per stage: the two 64-column boxes of the dh chunk + the x or W tile).
+// warp 0: TMA producer   warp 1: TMEM + MMA issue   warps 2-5: epilogue
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int DT_STAGES = 3, DT_STAGE_BYTES = DH_BYTES + TILE_BYTES, DT_THREADS = 192;
+constexpr size_t DT_SMEM = 1024 + (size_t)DT_STAGES * DT_STAGE_BYTES + TILE_BYTES + 256;
+}  // namespace
+
+__global__ void __launch_bounds__(DT_THREADS, 1)
+tfy_dense_bwd_tiled_kernel(const __grid_constant__ CUtensorMap map_dh, const __grid_constant__ CUtensorMap map_x,
+                           const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dw,
+                           const __grid_constant__ CUtensorMap map_dx, int n_u_tiles, int n_b_tiles, int want_dx) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem;                                            // [3] { dh box0, dh box1, tile }
+    uint8_t* s_out = ring + (size_t)DT_STAGES * DT_STAGE_BYTES;      // staging for the TMA store
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_out + TILE_BYTES);
+    uint64_t* empty = full + DT_STAGES;
+    uint64_t* acc_full = empty + DT_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * DB_N;
+    const int job = blockIdx.y;
+    const bool is_dw = job < n_u_tiles;
+    const int m0 = (is_dw ? job : job - n_u_tiles) * DB_M;           // first unit (dW) / batch row (dx) of the tile
+    const int n_chunks = is_dw ? n_b_tiles : n_u_tiles;              // K loop: batch chunks (dW) / unit chunks (dx)
+    if (!is_dw && !want_dx) return;
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_dh)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(is_dw ? &map_x : &map_w)) : "memory");
+        for (int st = 0; st < DT_STAGES; ++st) { d_mbar_init(&full[st], 1); d_mbar_init(&empty[st], 1); }
+        d_mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(d_smem_u32(tmem_slot)),
+                     "r"(64)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    tfy_pdl_sync();
+
+    if (warp == 0) {
+        if (d_elect_one()) {
+            for (int i = 0; i < n_chunks; ++i) {
+                const int st = i % DT_STAGES;
+                if (i >= DT_STAGES) d_mbar_wait(&empty[st], ((i / DT_STAGES) - 1) & 1);
+                uint8_t* dst = ring + (size_t)st * DT_STAGE_BYTES;
+                d_mbar_expect_tx(&full[st], DT_STAGE_BYTES);
+                const int k0 = i * DB_K;
+                if (is_dw) {           // dh rows = batch chunk, columns = this tile's units; x rows = batch chunk
+                    d_tma_load_2d(&map_dh, &full[st], dst, m0, k0);
+                    d_tma_load_2d(&map_dh, &full[st], dst + TILE_BYTES, m0 + 64, k0);
+                    d_tma_load_2d(&map_x, &full[st], dst + DH_BYTES, n0, k0);
+                } else {               // dh rows = this tile's batch rows, columns = unit chunk; W rows = unit chunk
+                    d_tma_load_2d(&map_dh, &full[st], dst, k0, m0);
+                    d_tma_load_2d(&map_dh, &full[st], dst + TILE_BYTES, k0 + 64, m0);
+                    d_tma_load_2d(&map_w, &full[st], dst + DH_BYTES, n0, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (d_elect_one()) {
+            const uint32_t idesc = d_idesc(DB_M, DB_N, is_dw ? 1 : 0, 1);
+            for (int i = 0; i < n_chunks; ++i) {
+                const int st = i % DT_STAGES;
+                d_mbar_wait(&full[st], (i / DT_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t dh0 = d_smem_u32(ring + (size_t)st * DT_STAGE_BYTES), t0 = dh0 + DH_BYTES;
+#pragma unroll
+                for (int k = 0; k < DB_K / 16; ++k) {
+                    const uint64_t adesc = is_dw ? d_desc(dh0 + k * 2048, TILE_BYTES, 1024)
+                                                 : d_desc(dh0 + (k >> 2) * TILE_BYTES + (k & 3) * 32, 0, 1024);
+                    const uint64_t bdesc = d_desc(t0 + k * 2048, 0, 1024);
+                    d_umma(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                d_commit(&empty[st]);
+            }
+            d_commit(acc_full);
+        }
+    } else {
+        const int quad = warp & 3;
+        d_mbar_wait(acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = quad * 32 + lane;
+        uint8_t* stage = s_out + row * 128;
+        uint32_t r[4][16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d_tmem_ld16(taddr + q * 16, r[q]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t* src = &r[ch >> 1][(ch & 1) * 8];
+            uint4 v;
+            v.x = tfy_pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]));
+            v.y = tfy_pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]));
+            v.z = tfy_pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]));
+            v.w = tfy_pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]));
+            *reinterpret_cast<uint4*>(stage + ((ch ^ (row & 7)) << 4)) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (quad == 2 && d_elect_one()) {
+            d_tma_store_2d(is_dw ? &map_dw : &map_dx, s_out, n0, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+    }
+}
+
 namespace {
 
 using DEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 DEncodeFn d_encode = nullptr;
-bool d_attr_set = false;
+bool d_attr_set = false, d_attr_set_tiled = false;
 
 bool d_load_encode() {
     if (d_encode) return true;
@@ -260,10 +385,30 @@ extern "C" {
 
 // dh: [B, U] bf16 (gradient wrt the layer's pre-activation), x: [B, I] bf16 (the layer's input), w: [U, I] bf16.
 // dw: [U, I] bf16 (overwritten), dx: [B, I] bf16 (overwritten; nullptr = first layer, no data gradient).
-// Envelope: B <= 128, U <= 128, U % 8 == 0, I % 8 == 0, 16-byte aligned pointers.  Returns -2 outside it.
+// Requirements: U % 8 == 0, I % 8 == 0, 16-byte aligned pointers (-2 / -3 otherwise).  batch <= 128 and units <= 128
+// take the single-shot kernel (one CTA per 64 in-features does both products); anything larger the tiled one.
 int tfy_dense_bwd(const void* dh, const void* x, const void* w, void* dw, void* dx, int B, int U, int I,
                   cudaStream_t s) {
-    if (B < 1 || B > DB_M || U < 8 || U > DB_M || (U & 7) || (I & 7) || I < 8) return -2;
+    if (B < 1 || U < 8 || (U & 7) || (I & 7) || I < 8) return -2;
+    if (B > DB_M || U > DB_M) {
+        if (((uintptr_t)dh | (uintptr_t)x | (uintptr_t)w | (uintptr_t)dw | (uintptr_t)dx) & 15) return -3;
+        if (!d_load_encode()) return -4;
+        if (!d_attr_set_tiled) {
+            if (cudaFuncSetAttribute(tfy_dense_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)DT_SMEM) != cudaSuccess)
+                return -5;
+            d_attr_set_tiled = true;
+        }
+        CUtensorMap mdh, mx, mw, mdw, mdx;
+        if (!d_make_map(&mdh, dh, B, U, U) || !d_make_map(&mx, x, B, I, I) || !d_make_map(&mw, w, U, I, I) ||
+            !d_make_map(&mdw, dw, U, I, I) || !d_make_map(&mdx, dx ? dx : dw, dx ? B : U, I, I))
+            return -6;
+        const int n_u = (U + DB_M - 1) / DB_M, n_b = (B + DB_M - 1) / DB_M;
+        dim3 grid((I + DB_N - 1) / DB_N, n_u + (dx ? n_b : 0));
+        tfy_launch_pdl((tfy_dense_bwd_tiled_kernel), grid, dim3(DT_THREADS), DT_SMEM, s, mdh, mx, mw, mdw, mdx, n_u, n_b,
+                       dx != nullptr ? 1 : 0);
+        return (int)cudaGetLastError();
+    }
     if (((uintptr_t)dh | (uintptr_t)x | (uintptr_t)w | (uintptr_t)dw | (uintptr_t)dx) & 15) return -3;
     if (!d_load_encode()) return -4;
     if (!d_attr_set) {

@@ -99,6 +99,15 @@ __device__ __forceinline__ void tfy_opt_update_rt(int opt_rt, float& p, float g,
         s2 = p2 * s2 + (1.f - p2) * g * g;
         const float denom = tfy_sqrt_approx(s2) * bc2_rsqrt + eps;
         p -= lr_bc1 * tfy_div_approx(s1, denom);
+    } else if (opt == TFY_OPT_FTRL) {
+        // FTRL-proximal (TF FtrlOptimizer, learning_rate_power = -0.5): s1 = n (squared-gradient accumulator),
+        // s2 = z (linear term); p1 = l1, p2 = l2, eps = beta
+        g += wd * p;
+        const float n_new = s1 + g * g;
+        const float sq_new = tfy_sqrt_approx(n_new);
+        s2 += g - (sq_new - tfy_sqrt_approx(s1)) * tfy_div_approx(p, lr);
+        s1 = n_new;
+        p = fabsf(s2) <= p1 ? 0.f : -tfy_div_approx(s2 - copysignf(p1, s2), tfy_div_approx(eps + sq_new, lr) + 2.f * p2);
     } else {  // Adagrad
         g += wd * p;
         s1 += g * g;
@@ -138,7 +147,7 @@ template <int OPT_T, int U>
 __device__ __forceinline__ void tfy_step_load_state(TfyStepRegs<U>& r, int opt_rt, const float* master, const float* s1,
                                                     const float* s2, size_t g_first, size_t stride, size_t g_hi) {
     const int opt = OPT_T >= 0 ? OPT_T : opt_rt;
-    const bool two = (opt == TFY_OPT_ADADELTA || opt == TFY_OPT_ADAM);
+    const bool two = (opt == TFY_OPT_ADADELTA || opt == TFY_OPT_ADAM || opt == TFY_OPT_FTRL);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const size_t g8 = g_first + (size_t)u * stride;
@@ -166,7 +175,7 @@ __device__ __forceinline__ void tfy_step_batch(const TfyCommCtx& c, int opt_rt, 
     constexpr int NG = 8 / GP::N;  // 16-byte packs per 8 gradient elements
     constexpr int NP = 8 / PP::N;
     const int opt = OPT_T >= 0 ? OPT_T : opt_rt;
-    const bool two = (opt == TFY_OPT_ADADELTA || opt == TFY_OPT_ADAM);
+    const bool two = (opt == TFY_OPT_ADADELTA || opt == TFY_OPT_ADAM || opt == TFY_OPT_FTRL);
     float g[U][8];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -292,6 +301,7 @@ __device__ __forceinline__ void tfy_overlap_role(const TfyOverlapStep& ov, int c
     if (ov.opt == TFY_OPT_SGD) TFY_ROLE_M(TFY_OPT_SGD);
     else if (ov.opt == TFY_OPT_ADADELTA) TFY_ROLE_M(TFY_OPT_ADADELTA);
     else if (ov.opt == TFY_OPT_ADAM) TFY_ROLE_M(TFY_OPT_ADAM);
+    else if (ov.opt == TFY_OPT_FTRL) TFY_ROLE_M(TFY_OPT_FTRL);
     else TFY_ROLE_M(TFY_OPT_ADAGRAD);
 #undef TFY_ROLE_M
 }

@@ -10,19 +10,35 @@
 //                  reduction (sum / mean) that consumes them
 //          GEMM  : weights stay remote and are streamed by TMA into the tcgen05 GEMM (tfy_gemm.cu)
 //   push   dense : every worker applies its gradient to the peer master with red/atom -- asynchronous,
-//                  lock free (TF's use_locking=False semantics), optimizer fused:
-//                    SGD      w   += -lr*g                         (red.v4.f32)
-//                    Adagrad  acc += g^2 ; w += -lr*g/(sqrt(acc)+eps)   (atom.v4.f32 returns old acc)
+//                  lock free (TF's use_locking=False semantics), optimizer fused, chosen PER VARIABLE (wide-and-deep
+//                  trains its linear tower with FTRL and its deep tower with Adagrad):
+//                    SGD      w   += -lr*g                                       (red.v4.f32)
+//                    Adagrad  acc += g^2 ; w += -lr*g/(sqrt(acc)+eps)            (atom.v4.f32 returns old acc)
+//                    FTRL     n += g^2 ; z += g - (sqrt(n')-sqrt(n))/lr * w ;    (two atom.v4.f32)
+//                             w  = |z|<=l1 ? 0 : -(z - sgn(z) l1) / ((beta+sqrt(n'))/lr + 2 l2)
+//                    Adam     m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;      (hogwild read-modify-write of m, v)
+//                             w += -lr_t m/(sqrt(v)+eps)                         (red.v4.f32)
 //                  and refreshes the bf16 shadow copy that the GEMM pull reads
 //          sparse: the same per touched embedding row (duplicate ids handled by the atomics)
 #include "tfy_common.cuh"
 
 struct TfyPsSeg {
     uint64_t remote_w;       // peer fp32 master
-    uint64_t remote_s1;      // peer fp32 optimizer slot (Adagrad accumulator), 0 if none
+    uint64_t remote_s1;      // peer fp32 optimizer slot 1 (Adagrad / FTRL accumulator, Adam m), 0 if none
+    uint64_t remote_s2;      // peer fp32 optimizer slot 2 (FTRL linear z, Adam v), 0 if none
     uint64_t remote_shadow;  // peer bf16 shadow of the master, 0 if none
     uint64_t local;          // local replica (pull destination) / local gradient (push source)
     uint64_t n;              // elements
+    int32_t opt;             // TfyOpt of THIS variable
+    float lr, eps, wd;
+    float p1, p2, p3;        // FTRL: l1, l2, beta | Adam: beta1, beta2, -
+    int32_t pad;
+};
+
+// optimizer hyper-parameters of one push (sparse rows: passed by value)
+struct TfyPsHyper {
+    int32_t opt;
+    float lr, eps, wd, p1, p2, p3, grad_scale;
 };
 
 namespace {
@@ -96,55 +112,126 @@ __global__ void __launch_bounds__(256) tfy_ps_pull_kernel(const TfyPsSeg* __rest
 }
 
 // ------------------------------------------------------------------------------------- dense push
-// opt: 0 SGD, 3 Adagrad (TfyOpt numbering).  grad_scale multiplies the local gradient first.
-template <typename GT, int OPT>
+namespace {
+
+__device__ __forceinline__ float4 f4_mul(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ void st_peer_f32x4(void* p, float4 v) {
+    asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float ftrl_w(float z, float n_new, float lr, float l1, float l2, float beta) {
+    if (fabsf(z) <= l1) return 0.f;
+    return -(z - copysignf(l1, z)) / ((beta + sqrtf(n_new)) / lr + 2.f * l2);
+}
+
+// One 4-element pack of an asynchronous update against the peer master: gv already scaled (and decayed).
+// Returns the new weights when they are known (needed for the bf16 shadow), via `neww`; `has_new` tells whether
+// the caller must refresh the shadow from them (true whenever a shadow exists).
+__device__ __forceinline__ void ps_apply4(int opt, float* w, float* s1, float* s2, float4 gv, float lr, float eps,
+                                          float p1, float p2, float p3, bool want_new, float4& neww) {
+    if (opt == TFY_OPT_FTRL) {
+        const float4 g2 = make_float4(gv.x * gv.x, gv.y * gv.y, gv.z * gv.z, gv.w * gv.w);
+        const float4 n_old = atom_add_f32x4(s1, g2);
+        const float4 n_new = make_float4(n_old.x + g2.x, n_old.y + g2.y, n_old.z + g2.z, n_old.w + g2.w);
+        const float4 wv = ld_peer_f32x4(w);
+        const float inv_lr = 1.f / lr;
+        const float4 dz = make_float4(gv.x - (sqrtf(n_new.x) - sqrtf(n_old.x)) * inv_lr * wv.x,
+                                      gv.y - (sqrtf(n_new.y) - sqrtf(n_old.y)) * inv_lr * wv.y,
+                                      gv.z - (sqrtf(n_new.z) - sqrtf(n_old.z)) * inv_lr * wv.z,
+                                      gv.w - (sqrtf(n_new.w) - sqrtf(n_old.w)) * inv_lr * wv.w);
+        const float4 z_old = atom_add_f32x4(s2, dz);
+        neww = make_float4(ftrl_w(z_old.x + dz.x, n_new.x, lr, p1, p2, p3), ftrl_w(z_old.y + dz.y, n_new.y, lr, p1, p2, p3),
+                           ftrl_w(z_old.z + dz.z, n_new.z, lr, p1, p2, p3), ftrl_w(z_old.w + dz.w, n_new.w, lr, p1, p2, p3));
+        st_peer_f32x4(w, neww);        // w is a pure function of (z, n): last writer wins, as in TF without locking
+        return;
+    }
+    float4 delta;
+    if (opt == TFY_OPT_ADAGRAD) {
+        const float4 g2 = make_float4(gv.x * gv.x, gv.y * gv.y, gv.z * gv.z, gv.w * gv.w);
+        const float4 old = atom_add_f32x4(s1, g2);
+        delta.x = -lr * gv.x / (sqrtf(old.x + g2.x) + eps);
+        delta.y = -lr * gv.y / (sqrtf(old.y + g2.y) + eps);
+        delta.z = -lr * gv.z / (sqrtf(old.z + g2.z) + eps);
+        delta.w = -lr * gv.w / (sqrtf(old.w + g2.w) + eps);
+    } else if (opt == TFY_OPT_ADAM) {
+        float4 m = ld_peer_f32x4(s1), v = ld_peer_f32x4(s2);
+        m = make_float4(p1 * m.x + (1.f - p1) * gv.x, p1 * m.y + (1.f - p1) * gv.y, p1 * m.z + (1.f - p1) * gv.z,
+                        p1 * m.w + (1.f - p1) * gv.w);
+        v = make_float4(p2 * v.x + (1.f - p2) * gv.x * gv.x, p2 * v.y + (1.f - p2) * gv.y * gv.y,
+                        p2 * v.z + (1.f - p2) * gv.z * gv.z, p2 * v.w + (1.f - p2) * gv.w * gv.w);
+        st_peer_f32x4(s1, m);
+        st_peer_f32x4(s2, v);
+        delta = make_float4(-lr * m.x / (sqrtf(v.x) + eps), -lr * m.y / (sqrtf(v.y) + eps),
+                            -lr * m.z / (sqrtf(v.z) + eps), -lr * m.w / (sqrtf(v.w) + eps));
+    } else {
+        delta = f4_mul(gv, -lr);
+    }
+    if (want_new) {
+        const float4 old = atom_add_f32x4(w, delta);
+        neww = make_float4(old.x + delta.x, old.y + delta.y, old.z + delta.z, old.w + delta.w);
+    } else {
+        red_add_f32x4(w, delta);
+    }
+}
+
+__device__ __forceinline__ float ps_apply1(int opt, float* w, float* s1, float* s2, float g, float lr, float eps, float p1,
+                                           float p2, float p3) {
+    if (opt == TFY_OPT_FTRL) {
+        const float n_old = atomicAdd(s1, g * g), n_new = n_old + g * g;
+        const float dz = g - (sqrtf(n_new) - sqrtf(n_old)) / lr * *w;
+        const float z = atomicAdd(s2, dz) + dz;
+        const float nw = ftrl_w(z, n_new, lr, p1, p2, p3);
+        *w = nw;
+        return nw;
+    }
+    float delta;
+    if (opt == TFY_OPT_ADAGRAD) {
+        const float old = atomicAdd(s1, g * g);
+        delta = -lr * g / (sqrtf(old + g * g) + eps);
+    } else if (opt == TFY_OPT_ADAM) {
+        const float m = p1 * *s1 + (1.f - p1) * g, v = p2 * *s2 + (1.f - p2) * g * g;
+        *s1 = m; *s2 = v;
+        delta = -lr * m / (sqrtf(v) + eps);
+    } else {
+        delta = -lr * g;
+    }
+    return atomicAdd(w, delta) + delta;
+}
+
+}  // namespace
+
+// The optimizer is a per-segment (= per-variable) runtime value (uniform per blockIdx.y).  grad_scale multiplies the
+// local gradient first; adam_scale[0] = sqrt(1-b2^t)/(1-b1^t) lives in device memory so that a captured CUDA graph
+// sees the bias correction advance.
+template <typename GT>
 __global__ void __launch_bounds__(256)
-tfy_ps_push_kernel(const TfyPsSeg* __restrict__ segs, float lr, float eps, float wd, float grad_scale) {
+tfy_ps_push_kernel(const TfyPsSeg* __restrict__ segs, float grad_scale, const float* __restrict__ adam_scale) {
     const TfyPsSeg sg = segs[blockIdx.y];
     float* w = reinterpret_cast<float*>(sg.remote_w);
-    float* acc = reinterpret_cast<float*>(sg.remote_s1);
+    float* s1 = reinterpret_cast<float*>(sg.remote_s1);
+    float* s2 = reinterpret_cast<float*>(sg.remote_s2);
     __nv_bfloat16* shadow = reinterpret_cast<__nv_bfloat16*>(sg.remote_shadow);
     const GT* g = reinterpret_cast<const GT*>(sg.local);
+    const int opt = sg.opt;
+    const float wd = sg.wd, eps = sg.eps, p1 = sg.p1, p2 = sg.p2, p3 = sg.p3;
+    const float lr = (opt == TFY_OPT_ADAM && adam_scale) ? sg.lr * adam_scale[0] : sg.lr;
     const size_t n4 = sg.n / 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 gv = ld_local4<GT>(g + i * 4);
-        gv.x *= grad_scale; gv.y *= grad_scale; gv.z *= grad_scale; gv.w *= grad_scale;
+        float4 gv = f4_mul(ld_local4<GT>(g + i * 4), grad_scale);
         if (wd != 0.f) {
             const float4 wv = ld_peer_f32x4(w + i * 4);
             gv.x += wd * wv.x; gv.y += wd * wv.y; gv.z += wd * wv.z; gv.w += wd * wv.w;
         }
-        float4 delta;
-        if (OPT == TFY_OPT_ADAGRAD) {
-            const float4 g2 = make_float4(gv.x * gv.x, gv.y * gv.y, gv.z * gv.z, gv.w * gv.w);
-            const float4 old = atom_add_f32x4(acc + i * 4, g2);
-            delta.x = -lr * gv.x / (sqrtf(old.x + g2.x) + eps);
-            delta.y = -lr * gv.y / (sqrtf(old.y + g2.y) + eps);
-            delta.z = -lr * gv.z / (sqrtf(old.z + g2.z) + eps);
-            delta.w = -lr * gv.w / (sqrtf(old.w + g2.w) + eps);
-        } else {
-            delta = make_float4(-lr * gv.x, -lr * gv.y, -lr * gv.z, -lr * gv.w);
-        }
-        if (shadow) {
-            const float4 old = atom_add_f32x4(w + i * 4, delta);
-            st_shadow_bf16x4(shadow + i * 4,
-                             make_float4(old.x + delta.x, old.y + delta.y, old.z + delta.z, old.w + delta.w));
-        } else {
-            red_add_f32x4(w + i * 4, delta);
-        }
+        float4 neww;
+        ps_apply4(opt, w + i * 4, s1 + i * 4, s2 + i * 4, gv, lr, eps, p1, p2, p3, shadow != nullptr, neww);
+        if (shadow) st_shadow_bf16x4(shadow + i * 4, neww);
     }
     if (blockIdx.x == 0) {   // scalar tail (n % 4 elements)
         for (size_t i = n4 * 4 + threadIdx.x; i < sg.n; i += blockDim.x) {
             float gv = (float)g[i] * grad_scale;
             if (wd != 0.f) gv += wd * w[i];
-            float delta;
-            if (OPT == TFY_OPT_ADAGRAD) {
-                const float old = atomicAdd(acc + i, gv * gv);
-                delta = -lr * gv / (sqrtf(old + gv * gv) + eps);
-            } else {
-                delta = -lr * gv;
-            }
-            const float oldw = atomicAdd(w + i, delta);
-            if (shadow) shadow[i] = __float2bfloat16(oldw + delta);
+            const float nw = ps_apply1(opt, w + i, s1 + i, s2 + i, gv, lr, eps, p1, p2, p3);
+            if (shadow) shadow[i] = __float2bfloat16(nw);
         }
     }
 }
@@ -172,37 +259,69 @@ tfy_ps_embedding_bag_kernel(const float* __restrict__ table, const long long* __
     }
 }
 
+// any D (the wide tower's per-bucket weights are [V, 1] tables): one element per thread
+template <typename OT>
+__global__ void __launch_bounds__(256)
+tfy_ps_embedding_bag_scalar_kernel(const float* __restrict__ table, const long long* __restrict__ ids,
+                                   OT* __restrict__ out, int B, int L, int D, long long V, int mean) {
+    const size_t total = (size_t)B * D;
+    const float scale = mean ? 1.f / (float)L : 1.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = i / D, d = i % D;
+        float acc = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const long long id = ids[(size_t)b * L + j];
+            if (id < 0 || id >= V) continue;
+            float v;
+            asm volatile("ld.global.relaxed.sys.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(table + (size_t)id * D + d)
+                         : "memory");
+            acc += v;
+        }
+        out[(size_t)b * D + d] = (OT)(acc * scale);
+    }
+}
+
 // ------------------------------------------------------------------------------------ sparse push
 // For every (b, j): row = ids[b, j]; g = dout[b, :] * (mean ? 1/L : 1) applied to the peer row.
-template <typename GT, int OPT>
+template <typename GT>
 __global__ void __launch_bounds__(256)
-tfy_ps_push_rows_kernel(float* __restrict__ table, float* __restrict__ acc_table, const long long* __restrict__ ids,
-                        const GT* __restrict__ dout, int B, int L, int D, long long V, int mean, float lr, float eps,
-                        float grad_scale) {
+tfy_ps_push_rows_kernel(float* __restrict__ table, float* __restrict__ s1_table, float* __restrict__ s2_table,
+                        const long long* __restrict__ ids, const GT* __restrict__ dout, int B, int L, int D, long long V,
+                        int mean, TfyPsHyper h, const float* __restrict__ adam_scale) {
     const int D4 = D / 4;
     const size_t total = (size_t)B * L * D4;
-    const float scale = (mean ? 1.f / (float)L : 1.f) * grad_scale;
+    const float scale = (mean ? 1.f / (float)L : 1.f) * h.grad_scale;
+    const float lr = (h.opt == TFY_OPT_ADAM && adam_scale) ? h.lr * adam_scale[0] : h.lr;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int d = (i % D4) * 4;
         const size_t bj = i / D4;
         const int b = bj / L;
         const long long id = ids[bj];
         if (id < 0 || id >= V) continue;
-        float4 gv = ld_local4<GT>(dout + (size_t)b * D + d);
-        gv.x *= scale; gv.y *= scale; gv.z *= scale; gv.w *= scale;
-        float* wrow = table + (size_t)id * D + d;
-        float4 delta;
-        if (OPT == TFY_OPT_ADAGRAD) {
-            const float4 g2 = make_float4(gv.x * gv.x, gv.y * gv.y, gv.z * gv.z, gv.w * gv.w);
-            const float4 old = atom_add_f32x4(acc_table + (size_t)id * D + d, g2);
-            delta.x = -lr * gv.x / (sqrtf(old.x + g2.x) + eps);
-            delta.y = -lr * gv.y / (sqrtf(old.y + g2.y) + eps);
-            delta.z = -lr * gv.z / (sqrtf(old.z + g2.z) + eps);
-            delta.w = -lr * gv.w / (sqrtf(old.w + g2.w) + eps);
-        } else {
-            delta = make_float4(-lr * gv.x, -lr * gv.y, -lr * gv.z, -lr * gv.w);
-        }
-        red_add_f32x4(wrow, delta);
+        const float4 gv = f4_mul(ld_local4<GT>(dout + (size_t)b * D + d), scale);
+        const size_t o = (size_t)id * D + d;
+        float4 unused;
+        ps_apply4(h.opt, table + o, s1_table + o, s2_table + o, gv, lr, h.eps, h.p1, h.p2, h.p3, false, unused);
+    }
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(256)
+tfy_ps_push_rows_scalar_kernel(float* __restrict__ table, float* __restrict__ s1_table, float* __restrict__ s2_table,
+                               const long long* __restrict__ ids, const GT* __restrict__ dout, int B, int L, int D,
+                               long long V, int mean, TfyPsHyper h, const float* __restrict__ adam_scale) {
+    const size_t total = (size_t)B * L * D;
+    const float scale = (mean ? 1.f / (float)L : 1.f) * h.grad_scale;
+    const float lr = (h.opt == TFY_OPT_ADAM && adam_scale) ? h.lr * adam_scale[0] : h.lr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int d = i % D;
+        const size_t bj = i / D;
+        const int b = bj / L;
+        const long long id = ids[bj];
+        if (id < 0 || id >= V) continue;
+        const size_t o = (size_t)id * D + d;
+        ps_apply1(h.opt, table + o, s1_table + o, s2_table + o, (float)dout[(size_t)b * D + d] * scale, lr, h.eps, h.p1,
+                  h.p2, h.p3);
     }
 }
 
@@ -232,23 +351,16 @@ int tfy_ps_pull(const TfyPsSeg* segs, int nseg, size_t max_n, int local_is_bf16,
     return (int)cudaGetLastError();
 }
 
-int tfy_ps_push(const TfyPsSeg* segs, int nseg, size_t max_n, int grad_is_bf16, int opt, float lr, float eps, float wd,
-                float grad_scale, cudaStream_t s) {
+// adam_scale: device pointer to sqrt(1-b2^t)/(1-b1^t) (may be nullptr when no segment uses Adam)
+int tfy_ps_push(const TfyPsSeg* segs, int nseg, size_t max_n, int grad_is_bf16, float grad_scale,
+                const float* adam_scale, cudaStream_t s) {
     if (nseg <= 0) return 0;
-    if (opt != TFY_OPT_SGD && opt != TFY_OPT_ADAGRAD) return -2;
     size_t gx = (max_n / 4 + 255) / 256;
     if (gx < 1) gx = 1;
     if (gx > 148 * 4) gx = 148 * 4;
     dim3 grid((unsigned)gx, nseg);
-#define TFY_PUSH(GT, O) tfy_ps_push_kernel<GT, O><<<grid, 256, 0, s>>>(segs, lr, eps, wd, grad_scale)
-    if (grad_is_bf16) {
-        if (opt == TFY_OPT_SGD) TFY_PUSH(__nv_bfloat16, TFY_OPT_SGD);
-        else TFY_PUSH(__nv_bfloat16, TFY_OPT_ADAGRAD);
-    } else {
-        if (opt == TFY_OPT_SGD) TFY_PUSH(float, TFY_OPT_SGD);
-        else TFY_PUSH(float, TFY_OPT_ADAGRAD);
-    }
-#undef TFY_PUSH
+    if (grad_is_bf16) tfy_ps_push_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(segs, grad_scale, adam_scale);
+    else tfy_ps_push_kernel<float><<<grid, 256, 0, s>>>(segs, grad_scale, adam_scale);
     return (int)cudaGetLastError();
 }
 
@@ -264,7 +376,18 @@ int tfy_ps_refresh_shadow(const TfyPsSeg* segs, int nseg, size_t max_n, cudaStre
 
 int tfy_ps_embedding_bag(const void* table, const void* ids, void* out, int out_is_bf16, int B, int L, int D,
                          long long V, int mean, cudaStream_t s) {
-    if (D % 4) return -2;
+    if (D % 4) {
+        size_t g1 = ((size_t)B * D + 255) / 256;
+        if (g1 < 1) g1 = 1;
+        if (g1 > 148 * 8) g1 = 148 * 8;
+        if (out_is_bf16)
+            tfy_ps_embedding_bag_scalar_kernel<__nv_bfloat16><<<(unsigned)g1, 256, 0, s>>>(
+                (const float*)table, (const long long*)ids, (__nv_bfloat16*)out, B, L, D, V, mean);
+        else
+            tfy_ps_embedding_bag_scalar_kernel<float><<<(unsigned)g1, 256, 0, s>>>(
+                (const float*)table, (const long long*)ids, (float*)out, B, L, D, V, mean);
+        return (int)cudaGetLastError();
+    }
     size_t gx = ((size_t)B * (D / 4) + 255) / 256;
     if (gx < 1) gx = 1;
     if (gx > 148 * 8) gx = 148 * 8;
@@ -277,26 +400,39 @@ int tfy_ps_embedding_bag(const void* table, const void* ids, void* out, int out_
     return (int)cudaGetLastError();
 }
 
-int tfy_ps_push_rows(void* table, void* acc_table, const void* ids, const void* dout, int grad_is_bf16, int B, int L,
-                     int D, long long V, int mean, int opt, float lr, float eps, float grad_scale, cudaStream_t s) {
-    if (D % 4) return -2;
-    if (opt != TFY_OPT_SGD && opt != TFY_OPT_ADAGRAD) return -3;
-    if (opt == TFY_OPT_ADAGRAD && !acc_table) return -4;
+int tfy_ps_push_rows(void* table, void* s1_table, void* s2_table, const void* ids, const void* dout, int grad_is_bf16,
+                     int B, int L, int D, long long V, int mean, int opt, float lr, float eps, float p1, float p2, float p3,
+                     float grad_scale, const float* adam_scale, cudaStream_t s) {
+    if (opt != TFY_OPT_SGD && opt != TFY_OPT_ADAGRAD && opt != TFY_OPT_ADAM && opt != TFY_OPT_FTRL) return -3;
+    if (opt != TFY_OPT_SGD && !s1_table) return -4;
+    if ((opt == TFY_OPT_ADAM || opt == TFY_OPT_FTRL) && !s2_table) return -4;
     size_t gx = ((size_t)B * L * (D / 4) + 255) / 256;
     if (gx < 1) gx = 1;
     if (gx > 148 * 8) gx = 148 * 8;
-#define TFY_PR(GT, O)                                                                                                 \
-    tfy_ps_push_rows_kernel<GT, O><<<(unsigned)gx, 256, 0, s>>>((float*)table, (float*)acc_table,                    \
-                                                                (const long long*)ids, (const GT*)dout, B, L, D, V,  \
-                                                                mean, lr, eps, grad_scale)
-    if (grad_is_bf16) {
-        if (opt == TFY_OPT_SGD) TFY_PR(__nv_bfloat16, TFY_OPT_SGD);
-        else TFY_PR(__nv_bfloat16, TFY_OPT_ADAGRAD);
-    } else {
-        if (opt == TFY_OPT_SGD) TFY_PR(float, TFY_OPT_SGD);
-        else TFY_PR(float, TFY_OPT_ADAGRAD);
+    TfyPsHyper h;
+    h.opt = opt; h.lr = lr; h.eps = eps; h.wd = 0.f; h.p1 = p1; h.p2 = p2; h.p3 = p3; h.grad_scale = grad_scale;
+    if (D % 4) {
+        size_t g1 = ((size_t)B * L * D + 255) / 256;
+        if (g1 < 1) g1 = 1;
+        if (g1 > 148 * 8) g1 = 148 * 8;
+        if (grad_is_bf16)
+            tfy_ps_push_rows_scalar_kernel<__nv_bfloat16><<<(unsigned)g1, 256, 0, s>>>(
+                (float*)table, (float*)s1_table, (float*)s2_table, (const long long*)ids, (const __nv_bfloat16*)dout, B,
+                L, D, V, mean, h, adam_scale);
+        else
+            tfy_ps_push_rows_scalar_kernel<float><<<(unsigned)g1, 256, 0, s>>>(
+                (float*)table, (float*)s1_table, (float*)s2_table, (const long long*)ids, (const float*)dout, B, L, D, V,
+                mean, h, adam_scale);
+        return (int)cudaGetLastError();
     }
-#undef TFY_PR
+    if (grad_is_bf16)
+        tfy_ps_push_rows_kernel<__nv_bfloat16><<<(unsigned)gx, 256, 0, s>>>(
+            (float*)table, (float*)s1_table, (float*)s2_table, (const long long*)ids, (const __nv_bfloat16*)dout, B, L, D,
+            V, mean, h, adam_scale);
+    else
+        tfy_ps_push_rows_kernel<float><<<(unsigned)gx, 256, 0, s>>>((float*)table, (float*)s1_table, (float*)s2_table,
+                                                                    (const long long*)ids, (const float*)dout, B, L, D,
+                                                                    V, mean, h, adam_scale);
     return (int)cudaGetLastError();
 }
 

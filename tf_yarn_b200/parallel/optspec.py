@@ -1,14 +1,14 @@
 """Fused-optimizer hyper-parameter description (no CUDA dependency)."""
 from __future__ import annotations
 
-OPT_SGD, OPT_ADADELTA, OPT_ADAM, OPT_ADAGRAD = 0, 1, 2, 3
+OPT_SGD, OPT_ADADELTA, OPT_ADAM, OPT_ADAGRAD, OPT_FTRL = 0, 1, 2, 3, 4
 
 
 class OptimizerSpec:
     """Hyper-parameters of a fused optimizer (device-independent description)."""
 
     KINDS = {"sgd": OPT_SGD, "adadelta": OPT_ADADELTA, "adam": OPT_ADAM,
-             "adamw": OPT_ADAM, "adagrad": OPT_ADAGRAD}
+             "adamw": OPT_ADAM, "adagrad": OPT_ADAGRAD, "ftrl": OPT_FTRL}
 
     def __init__(self, kind: str, lr: float, p1: float = 0.0, p2: float = 0.0, eps: float = 1e-7,
                  weight_decay: float = 0.0, flags: int = 0, init_s1: float = 0.0):
@@ -26,7 +26,7 @@ class OptimizerSpec:
 
     @property
     def n_states(self) -> int:
-        return 2 if self.kind in ("adadelta", "adam", "adamw") else 1
+        return 2 if self.kind in ("adadelta", "adam", "adamw", "ftrl") else 1
 
     @staticmethod
     def sgd(lr, momentum=0.0, dampening=0.0, nesterov=False, weight_decay=0.0):
@@ -43,3 +43,9 @@ class OptimizerSpec:
     @staticmethod
     def adagrad(lr=1e-2, eps=1e-10, weight_decay=0.0, initial_accumulator_value=0.0):
         return OptimizerSpec("adagrad", lr, 0.0, 0.0, eps, weight_decay, init_s1=initial_accumulator_value)
+
+    @staticmethod
+    def ftrl(lr=1e-3, l1=0.0, l2=0.0, beta=0.0, initial_accumulator_value=0.1, weight_decay=0.0):
+        """FTRL-proximal with learning_rate_power = -0.5 (TF's FtrlOptimizer default): s1 = accumulator n
+        (initial_accumulator_value), s2 = linear z; p1 = l1, p2 = l2, eps carries beta."""
+        return OptimizerSpec("ftrl", lr, l1, l2, beta, weight_decay, init_s1=initial_accumulator_value)
