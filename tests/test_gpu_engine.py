@@ -384,3 +384,22 @@ def test_overlapped_exchange_matches_single_launch(monkeypatch):
     torch.testing.assert_close(s1, s0, rtol=1e-5, atol=1e-9)
     torch.testing.assert_close(p1.float(), p0.float(), rtol=1e-2, atol=1e-4)
     assert eng1.fused.step_count == eng0.fused.step_count == 8
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 768, 512), (1000, 520, 264), (4096, 1024, 128), (130, 300, 72)])
+def test_tcgen05_2cta_gemm_matches_fp32_reference(shape):
+    """Persistent cta_group::2 GEMM (256x256 tiles of a CTA pair, double-buffered TMEM, TMA-store epilogue) vs fp32."""
+    from tf_yarn_b200.ops.gemm import gemm_bf16
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 7 * K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) * 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g).bfloat16()
+    ref = a.float() @ b.float().t()
+    out = gemm_bf16(a, b, impl="2cta")
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() < max(0.02 * K ** 0.5 * 0.25 + 0.01, 0.01 * ref.abs().max().item())
+    out2 = gemm_bf16(a, b, bias=bias, relu=True, impl="2cta")
+    ref2 = torch.relu(ref + bias.float())
+    torch.cuda.synchronize()
+    assert (out2.float() - ref2).abs().max().item() < max(0.02 * K ** 0.5 * 0.25 + 0.02, 0.01 * ref2.abs().max().item())
