@@ -75,15 +75,22 @@ class BenchHook:
         import torch
         self.i += 1
         i, W, K = self.i, self.warmup, self.steps
+        cuda = torch.cuda.is_available()
         if i == W:
-            torch.cuda.synchronize()
+            if cuda:
+                torch.cuda.synchronize()
             self._barrier("start")
-            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            self.ev[0].record()
+            if cuda:
+                self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                self.ev[0].record()
+            self.t0 = time.perf_counter()
         elif i == W + K:
-            self.ev[1].record()
-            self.ev[1].synchronize()
-            self.res["device_ms"] = self.ev[0].elapsed_time(self.ev[1])
+            if cuda:
+                self.ev[1].record()
+                self.ev[1].synchronize()
+                self.res["device_ms"] = self.ev[0].elapsed_time(self.ev[1])
+            else:                                   # CPU plumbing run (no GPU in the container): wall clock
+                self.res["device_ms"] = (time.perf_counter() - self.t0) * 1e3
             self._barrier("e2e")
             self.t0 = time.perf_counter()
         elif W + K < i <= W + 2 * K:
@@ -91,7 +98,8 @@ class BenchHook:
             if loss is not None:
                 self.res["final_loss"] = float(loss)            # D2H read of the step's loss, every step
             if i == W + 2 * K:
-                torch.cuda.synchronize()
+                if cuda:
+                    torch.cuda.synchronize()
                 self.res["e2e_ms"] = (time.perf_counter() - self.t0) * 1e3
                 ps = getattr(ctx.estimator, "_ps", None)
                 if ps is not None and hasattr(ps, "traffic_per_step"):
@@ -158,8 +166,27 @@ def run(args):
     sampler.start()
     sampler.arm(True)
     t0 = time.time()
+    # watchdog: a wedged job must not eat the GPU lease -- dump the task logs and give up
+    import glob
+    import threading
+
+    def _watchdog():
+        sys.stderr.write("bench watchdog: the job did not finish in time; task logs follow\n")
+        for log in sorted(glob.glob("/tmp/tfy_application_*/logs/*/task.log"), key=os.path.getmtime)[-12:]:
+            try:
+                tail = open(log, errors="replace").read()[-1500:]
+            except OSError:
+                continue
+            sys.stderr.write(f"==== {log}\n{tail}\n")
+        print(json.dumps({"impl": "ours", "config": "wide_deep", "error": "timeout", "n_gpus": n}), flush=True)
+        os._exit(1)
+
+    wd_timer = threading.Timer(float(os.environ.get("TFY_BENCH_TIMEOUT", "240")), _watchdog)
+    wd_timer.daemon = True
+    wd_timer.start()
     run_on_yarn(make_experiment_fn(model_dir, steps, warm, n_trainers, out_dir), specs,
                 env={"TFY_ARENA_MB": "2048", "TFY_FUSION_MB": "16"})
+    wd_timer.cancel()
     wall = time.time() - t0
     clocks = sampler.stop()
     res = []

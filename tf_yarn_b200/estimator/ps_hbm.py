@@ -40,7 +40,8 @@ native.declare("tfy_ps_refresh_shadow", [_vp, _i, _sz, _vp])
 native.declare("tfy_dense_bwd", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_ps_embedding_bag", [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp])
 native.declare("tfy_ps_push_rows", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _i, _f, _f, _f, _f, _f, _f, _vp,
-                                    _vp])
+                                    _i, _vp])
+native.declare("tfy_ps_gather_gemm", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp])
 
 OPT_CODES = {"sgd": native.OPT_SGD, "adagrad": native.OPT_ADAGRAD, "adam": native.OPT_ADAM,
              "ftrl": native.OPT_FTRL}
@@ -51,7 +52,8 @@ class PsSeg(ctypes.Structure):
     _fields_ = [("remote_w", ctypes.c_uint64), ("remote_s1", ctypes.c_uint64), ("remote_s2", ctypes.c_uint64),
                 ("remote_shadow", ctypes.c_uint64), ("local", ctypes.c_uint64), ("n", ctypes.c_uint64),
                 ("opt", ctypes.c_int32), ("lr", ctypes.c_float), ("eps", ctypes.c_float), ("wd", ctypes.c_float),
-                ("p1", ctypes.c_float), ("p2", ctypes.c_float), ("p3", ctypes.c_float), ("pad", ctypes.c_int32)]
+                ("p1", ctypes.c_float), ("p2", ctypes.c_float), ("p3", ctypes.c_float), ("pad", ctypes.c_int32),
+                ("cols", ctypes.c_uint32), ("shadow_ld", ctypes.c_uint32)]
 
 
 def cluster_ranks(cluster) -> Dict[str, int]:
@@ -78,7 +80,8 @@ def shard_bytes(layout: ps_cpu.Layout) -> int:
     worst = 0
     for ps in range(layout.n_ps):
         elems = layout.shard_elems[ps]
-        worst = max(worst, elems * 4 + elems * 2 + 4096)
+        rows = sum(int(s[0]) for (_, s), o in zip(layout.variables, layout.owner) if o == ps and len(s) == 2)
+        worst = max(worst, elems * 4 + elems * 2 + rows * 16 + 4096)       # fp32 area + (row-padded) bf16 shadows
     return (worst + 4095) // 4096 * 4096
 
 
@@ -137,13 +140,24 @@ class HbmConnection:
         ps = lay.owner[i]
         return self.ps_base[ps] + 4 * lay.shard_elems[ps] + 2 * self._shadow_off(i)
 
+    def shadow_ld(self, i: int) -> int:
+        """Row pitch (elements) of variable i's bf16 shadow: 2-D weights are stored with rows padded to a multiple
+        of 8 elements so that a TMA tensor map can describe them whatever in_features is (0 = flat)."""
+        shape = self.layout.variables[i][1]
+        return (int(shape[1]) + 7) // 8 * 8 if len(shape) == 2 else 0
+
+    def _shadow_elems(self, i: int) -> int:
+        shape = self.layout.variables[i][1]
+        ld = self.shadow_ld(i)
+        return (int(shape[0]) * ld + 7) // 8 * 8 if ld else self.layout.padded(i)
+
     def _shadow_off(self, i: int) -> int:
-        """Element offset of variable i inside its ps's bf16 shadow area (padded sizes, layout order)."""
+        """Element offset of variable i inside its ps's bf16 shadow area (layout order)."""
         lay = self.layout
         off = 0
         for j in range(i):
             if lay.owner[j] == lay.owner[i]:
-                off += lay.padded(j)
+                off += self._shadow_elems(j)
         return off
 
     def remote_tensor(self, i: int, slot: int = 0) -> torch.Tensor:
@@ -157,8 +171,8 @@ class HbmConnection:
         for mod in network.modules():
             if isinstance(mod, nn.EmbeddingBag) and id(mod.weight) in by_param and mod.mode in ("sum", "mean"):
                 self.sparse[by_param[id(mod.weight)]] = mod
-            elif isinstance(mod, nn.Linear) and id(mod.weight) in by_param and mod.in_features % 8 == 0 \
-                    and mod.out_features >= 8 and mod.out_features % 8 == 0:
+            elif isinstance(mod, nn.Linear) and id(mod.weight) in by_param and mod.out_features >= 8 \
+                    and mod.out_features % 8 == 0:
                 self.gemm[by_param[id(mod.weight)]] = mod
 
     def _make_segs(self, for_push: bool, idx: Optional[List[int]] = None):
@@ -178,6 +192,9 @@ class HbmConnection:
             # FTRL: l1, l2, beta (OptimizerSpec.ftrl keeps beta in eps) | Adam: beta1, beta2
             segs[k].p1, segs[k].p2 = float(h["p1"]), float(h["p2"])
             segs[k].p3 = float(h["eps"]) if self.layout.kinds[i] == "ftrl" else 0.0
+            ld = self.shadow_ld(i) if i in self.gemm else 0
+            segs[k].cols = int(self.layout.variables[i][1][1]) if ld else 0
+            segs[k].shadow_ld = ld
         dev_segs = torch.frombuffer(bytearray(bytes(segs)), dtype=torch.uint8).to(self.device)
         return dev_segs
 
@@ -189,6 +206,7 @@ class HbmConnection:
             mod.forward = _make_bag_forward(conn, idx, mod)
         for idx, mod in self.gemm.items():
             mod.forward = _make_linear_forward(conn, idx, mod)
+        self.fused_first = _try_fuse_first_layer(conn, network)
 
     # ------------------------------------------------------------------ pull / push
     def pull(self, network: nn.Module) -> None:
@@ -289,7 +307,7 @@ def _make_bag_forward(conn: HbmConnection, idx: int, mod: nn.EmbeddingBag):
             p3 = float(h["eps"]) if lay.kinds[idx] == "ftrl" else 0.0
             native.check(lib.tfy_ps_push_rows(conn.master_ptr(idx), s1, s2, ids.data_ptr(), dout.data_ptr(), 0, B, L, D,
                                               V, mean, conn.var_opt[idx], float(h["lr"]), float(h["eps"]),
-                                              float(h["p1"]), float(h["p2"]), p3, 1.0, conn.adam_scale.data_ptr(),
+                                              float(h["p1"]), float(h["p2"]), p3, 1.0, conn.adam_scale.data_ptr(), 0,
                                               torch.cuda.current_stream().cuda_stream), "tfy_ps_push_rows")
             conn.account(push=B * L * D * 4 * (1 + lay.var_slots[idx]))
             return None, None
@@ -304,15 +322,20 @@ def _make_bag_forward(conn: HbmConnection, idx: int, mod: nn.EmbeddingBag):
 def _make_linear_forward(conn: HbmConnection, idx: int, mod: nn.Linear):
     from tf_yarn_b200.ops.gemm import gemm_bf16
     N, K = mod.out_features, mod.in_features
+    Kp = conn.shadow_ld(idx)                 # row pitch of the remote bf16 shadow (K rounded up to 8; pad columns = 0)
     shadow = conn.shadow_ptr(idx)
 
     class _PSLinear(torch.autograd.Function):
         @staticmethod
         def forward(ctx, x, weight, bias):
-            xb = x.to(torch.bfloat16).contiguous()
+            if Kp == K:
+                xb = x.to(torch.bfloat16).contiguous()
+            else:                            # TMA needs 16-byte row pitches: zero-pad the activations like the shadow
+                xb = torch.zeros((x.shape[0], Kp), dtype=torch.bfloat16, device=x.device)
+                xb[:, :K] = x
             y = gemm_bf16(xb, None, bias=bias.to(torch.bfloat16) if bias is not None else None, b_ptr=shadow,
-                          b_rows=N, b_ld=K)                     # weights stream from the ps rank over NVLink
-            conn.account(pull=N * K * 2)
+                          b_rows=N, b_ld=Kp, impl="1cta")       # weights stream from the ps rank over NVLink
+            conn.account(pull=N * Kp * 2)
             ctx.save_for_backward(xb, weight)
             ctx.has_bias = bias is not None
             return y.to(x.dtype)
@@ -322,19 +345,134 @@ def _make_linear_forward(conn: HbmConnection, idx: int, mod: nn.Linear):
             xb, weight = ctx.saved_tensors
             B = xb.shape[0]
             dyb = dy.to(torch.bfloat16).contiguous()
-            dw = torch.empty((N, K), dtype=torch.bfloat16, device=dy.device)
-            dx = torch.empty((B, K), dtype=torch.bfloat16, device=dy.device) if ctx.needs_input_grad[0] else None
+            dw = torch.empty((N, Kp), dtype=torch.bfloat16, device=dy.device)
+            dx = torch.empty((B, Kp), dtype=torch.bfloat16, device=dy.device) if ctx.needs_input_grad[0] else None
             # dW = dy^T x and dx = dy W in one tcgen05 kernel; W is the ps rank's bf16 shadow, read over NVLink
             native.check(conn.lib.tfy_dense_bwd(dyb.data_ptr(), xb.data_ptr(), shadow, dw.data_ptr(),
-                                                dx.data_ptr() if dx is not None else None, B, N, K,
+                                                dx.data_ptr() if dx is not None else None, B, N, Kp,
                                                 torch.cuda.current_stream().cuda_stream), "tfy_dense_bwd")
-            conn.account(pull=N * K * 2 if dx is not None else 0)
+            conn.account(pull=N * Kp * 2 if dx is not None else 0)
             db = dy.float().sum(0) if ctx.has_bias else None
-            return (dx.to(dy.dtype) if dx is not None else None), dw.to(weight.dtype), db
+            gx = dx[:, :K].to(dy.dtype) if dx is not None else None
+            return gx, dw[:, :K].to(weight.dtype), db
 
     def forward(x):
         return _PSLinear.apply(x, mod.weight, mod.bias)
     return forward
+
+
+def _try_fuse_first_layer(conn: HbmConnection, network: nn.Module) -> bool:
+    """K5: fuse the sparse pull of the embedding rows INTO the first deep GEMM (ops/csrc/tfy_ps_gemm.cu).
+
+    Pattern (the canned wide-and-deep / DNN networks): ``network.dense_features`` concatenates embedding columns
+    of dimension 64 with one id per example followed by numeric columns (<= 64 values in total), and
+    ``network.hidden[0]`` is a Linear served by the remote-weight GEMM.  The gather of the rows from the ps ranks'
+    HBM becomes the A-operand producer of that GEMM; the backward (dW, dx) is one tcgen05 kernel against the same
+    remote shadow, and the row gradients are pushed straight out of its dx.  TFY_PS_FUSE_FIRST=0 disables it."""
+    from tf_yarn_b200.estimator import feature_column as fc
+    if os.environ.get("TFY_PS_FUSE_FIRST", "1") == "0":
+        return False
+    df, hidden = getattr(network, "dense_features", None), getattr(network, "hidden", None)
+    if not isinstance(df, fc.DenseFeatures) or not hidden or not isinstance(hidden[0], nn.Linear):
+        return False
+    lin = hidden[0]
+    by_param = {id(p): i for i, p in enumerate(conn.params)}
+    widx = by_param.get(id(lin.weight))
+    if widx is None or widx not in conn.gemm or lin.bias is None:
+        return False
+    emb_cols, num_cols, seen_numeric = [], [], False
+    for c in df.columns:
+        if isinstance(c, fc.EmbeddingColumn) and not seen_numeric and c.dimension == 64:
+            emb_cols.append(c)
+        elif isinstance(c, fc.NumericColumn):
+            seen_numeric = True
+            num_cols.append(c)
+        else:
+            return False                     # embeddings must come first, all of dimension 64
+    T, n_num = len(emb_cols), sum(c.dim for c in num_cols)
+    if T == 0 or n_num > 64 or lin.in_features != 64 * T + n_num:
+        return False
+    tables_idx = []
+    for c in emb_cols:
+        emb = df.embeddings[c.categorical_column.key]
+        ti = by_param.get(id(emb.weight))
+        if ti is None or ti not in conn.sparse or emb.mode not in ("sum", "mean"):
+            return False
+        tables_idx.append(ti)
+    V = emb_cols[0].categorical_column.num_buckets
+    if any(c.categorical_column.num_buckets != V for c in emb_cols):
+        return False
+    dev = conn.device
+    N, K, Kp = lin.out_features, lin.in_features, conn.shadow_ld(widx)
+    shadow = conn.shadow_ptr(widx)
+    table_ptrs = torch.tensor([conn.master_ptr(ti) for ti in tables_idx], dtype=torch.int64, device=dev)
+    lib, lay = conn.lib, conn.layout
+
+    class _FusedFirst(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, ids, numeric, weight, bias):
+            B = ids.shape[1]
+            xbuf = torch.zeros((B, Kp), dtype=torch.bfloat16, device=dev)
+            y = torch.empty((B, N), dtype=torch.bfloat16, device=dev)
+            bb = bias.to(torch.bfloat16)
+            native.check(lib.tfy_ps_gather_gemm(shadow, table_ptrs.data_ptr(), ids.data_ptr(),
+                                                numeric.data_ptr() if numeric is not None else None, bb.data_ptr(),
+                                                xbuf.data_ptr(), y.data_ptr(), B, N, T, n_num, Kp, V,
+                                                torch.cuda.current_stream().cuda_stream), "tfy_ps_gather_gemm")
+            conn.account(pull=B * T * 64 * 4 + N * Kp * 2)
+            ctx.save_for_backward(xbuf, ids, weight)
+            return y.to(weight.dtype)
+
+        @staticmethod
+        def backward(ctx, dy):
+            xbuf, ids, weight = ctx.saved_tensors
+            B = xbuf.shape[0]
+            s = torch.cuda.current_stream().cuda_stream
+            dyb = dy.to(torch.bfloat16).contiguous()
+            dw = torch.empty((N, Kp), dtype=torch.bfloat16, device=dev)
+            dx = torch.empty((B, Kp), dtype=torch.bfloat16, device=dev)
+            native.check(lib.tfy_dense_bwd(dyb.data_ptr(), xbuf.data_ptr(), shadow, dw.data_ptr(), dx.data_ptr(), B, N,
+                                           Kp, s), "tfy_dense_bwd")
+            conn.account(pull=N * Kp * 2)
+            for t, ti in enumerate(tables_idx):          # sparse push of table t from columns [64 t, 64 t + 64) of dx
+                h = lay.hypers[ti]
+                s1 = conn.master_ptr(ti, 1) if lay.var_slots[ti] >= 1 else None
+                s2 = conn.master_ptr(ti, 2) if lay.var_slots[ti] >= 2 else None
+                p3 = float(h["eps"]) if lay.kinds[ti] == "ftrl" else 0.0
+                native.check(lib.tfy_ps_push_rows(
+                    conn.master_ptr(ti), s1, s2, ids[t].data_ptr(), dx.data_ptr() + 2 * 64 * t, 1, B, 1, 64, V, 0,
+                    conn.var_opt[ti], float(h["lr"]), float(h["eps"]), float(h["p1"]), float(h["p2"]), p3, 1.0,
+                    conn.adam_scale.data_ptr(), Kp, s), "tfy_ps_push_rows")
+                conn.account(push=B * 64 * 4 * (1 + lay.var_slots[ti]))
+            return None, None, dw[:, :K].to(weight.dtype), dy.float().sum(0).to(weight.dtype)
+
+    class _Deferred:
+        """What the patched DenseFeatures returns: the raw inputs of the fused first layer."""
+
+        def __init__(self, ids, numeric):
+            self.ids, self.numeric = ids, numeric
+
+        def to(self, *a, **k):
+            return self
+
+    def df_forward(features):
+        ids = torch.stack([fc._ids(c.categorical_column, features[c.categorical_column.key]).reshape(-1)
+                           for c in emb_cols]).contiguous()
+        numeric = None
+        if num_cols:
+            parts = [features[c.key].reshape(features[c.key].shape[0], -1).float() for c in num_cols]
+            numeric = (parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)).contiguous()
+        return _Deferred(ids, numeric)
+
+    def lin_forward(x):
+        if isinstance(x, _Deferred):
+            return _FusedFirst.apply(x.ids, x.numeric, lin.weight, lin.bias)
+        return _make_linear_forward(conn, widx, lin)(x)
+
+    df.forward = df_forward
+    lin.forward = lin_forward
+    logger.info("K5: embedding gather of %d tables fused into the first deep GEMM (%d -> %d)", T, K, N)
+    return True
 
 
 # ---------------------------------------------------------------------------------------------

@@ -19,7 +19,9 @@ def feature_columns(vocab: int = 100_000, emb_dim: int = 64, n_cat: int = N_CATE
     from tf_yarn_b200.estimator import feature_column as fc
     numeric = [fc.numeric_column("numeric", shape=(n_num,))]
     cats = [fc.categorical_column_with_hash_bucket(f"c{i}", vocab) for i in range(n_cat)]
-    deep = numeric + [fc.embedding_column(c, emb_dim) for c in cats]
+    # embeddings first, numeric last: every embedding then starts at a multiple of 64 columns of the first deep
+    # layer's input, which is what lets the HBM parameter server fuse the row gather into that layer's GEMM
+    deep = [fc.embedding_column(c, emb_dim) for c in cats] + numeric
     wide = numeric + cats
     return wide, deep
 

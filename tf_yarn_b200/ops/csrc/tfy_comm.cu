@@ -161,20 +161,26 @@ __global__ void __launch_bounds__(256)
 tfy_fused_step_kernel(TfyCommCtx c, uint64_t grad_off, uint64_t param_off, size_t shard_n,
                       float* __restrict__ master, float* __restrict__ s1, float* __restrict__ s2,
                       TfyOptHyper* __restrict__ hp, int zero_grads, size_t g_lo, size_t g_hi, int advance) {
-    tfy_pdl_sync();
+    // Everything up to tfy_pdl_wait() only touches data this kernel itself wrote in the previous step (hyper
+    // block, master, optimizer state): with programmatic dependent launch it overlaps the tail of the last
+    // backward kernel.
+    tfy_pdl_launch_dependents();
     using GP = TfyPack<GT>;
     constexpr int NG = 8 / GP::N;  // 16-byte packs per 8 gradient elements
-    const TfyStepConsts k = tfy_step_consts(hp, c.world, OPT);
-    const int step = hp->step;
-    const uint32_t ep = (MODE != TFY_MODE_LOCAL) ? tfy_grid_epoch(c) : 0u;
     const size_t shard_start = (MODE == TFY_MODE_LOCAL) ? 0 : shard_n * (size_t)c.rank;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t tid = g_lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 
-    // The owned master / optimizer-state shard does not depend on the peers: its loads are issued BEFORE the
-    // cross-GPU barrier and before the (2-3 us) in-switch reduction, so their latency hides behind both.
+    // The owned master / optimizer-state shard does not depend on the peers (nor, with programmatic dependent
+    // launch, on the preceding backward kernel): its loads are issued BEFORE the dependency wait, the cross-GPU
+    // barrier and the (2-3 us) in-switch reduction, so their latency hides behind all three.  (TFY_PDL_K4=1
+    // assumes a different kernel separates two fused-step launches on the stream -- true for every train step.)
     TfyStepRegs<U> r;
     tfy_step_load_state<OPT, U>(r, OPT, master, s1, s2, tid, nthreads, g_hi);
+    tfy_pdl_wait();                                     // the gradients of THIS rank are complete
+    const TfyStepConsts k = tfy_step_consts(hp, c.world, OPT);
+    const int step = hp->step;
+    const uint32_t ep = (MODE != TFY_MODE_LOCAL) ? tfy_grid_epoch(c) : 0u;
 
     if (MODE != TFY_MODE_LOCAL) tfy_grid_entry(c, ep);  // all ranks finished backward
 
@@ -304,7 +310,7 @@ static int tfy_fused_step_groups(const TfyCommCtx* c, int grad_dtype, int param_
                                         mode == TFY_MODE_LOCAL ? 148 * 6 : 148 * 2);
     if (grid > TFY_MAX_BLOCKS) grid = TFY_MAX_BLOCKS;
 #define TFY_FS4(GT, PT, O, M, U)                                                                                 \
-    tfy_launch_pdl((tfy_fused_step_kernel<GT, PT, O, M, U>), dim3(grid), dim3(block), 0, s, *c, grad_off, param_off, \
+    tfy_launch_pdl_if(tfy_pdl_enabled() || tfy_pdl_k4_enabled(), (tfy_fused_step_kernel<GT, PT, O, M, U>), dim3(grid), dim3(block), 0, s, *c, grad_off, param_off, \
                    shard_n, master, s1, s2, hp, zero_grads, g_lo, g_hi, advance)
 #define TFY_FS3(GT, PT, O)                                                  \
     do {                                                                    \

@@ -300,6 +300,39 @@ static inline bool tfy_pdl_enabled() {
     return v != 0;
 }
 
+// Per-kernel opt-in (TFY_PDL_K4=1): only the fused step is launched with programmatic stream serialisation, so its
+// launch latency and the prefetch of its optimizer state overlap the tail of the last backward kernel.
+static inline bool tfy_pdl_k4_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TFY_PDL_K4");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void tfy_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void tfy_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tfy_launch_pdl_if(bool enable, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                            cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = enable ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t tfy_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                          Args... args) {

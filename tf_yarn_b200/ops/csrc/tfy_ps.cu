@@ -33,6 +33,9 @@ struct TfyPsSeg {
     float lr, eps, wd;
     float p1, p2, p3;        // FTRL: l1, l2, beta | Adam: beta1, beta2, -
     int32_t pad;
+    // bf16 shadow of a 2-D weight [rows, cols]: rows are `shadow_ld` elements apart (cols rounded up to 8 so that
+    // a TMA tensor map can describe it); cols == 0 means "flat, same indexing as the master"
+    uint32_t cols, shadow_ld;
 };
 
 // optimizer hyper-parameters of one push (sparse rows: passed by value)
@@ -64,11 +67,27 @@ __device__ __forceinline__ float4 atom_add_f32x4(void* p, float4 v) {
                  : "memory");
     return o;
 }
+// element index of the master -> element index of the (row-padded) shadow
+__device__ __forceinline__ size_t shadow_index(size_t i, uint32_t cols, uint32_t ld) {
+    return cols ? (i / cols) * (size_t)ld + (i % cols) : i;
+}
+__device__ __forceinline__ void st_shadow4(__nv_bfloat16* shadow, size_t i, float4 v, uint32_t cols, uint32_t ld);
+
 __device__ __forceinline__ void st_shadow_bf16x4(void* p, float4 v) {
     uint2 u;
     u.x = tfy_pack_bf16x2(v.x, v.y);
     u.y = tfy_pack_bf16x2(v.z, v.w);
     asm volatile("st.global.relaxed.sys.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(u.x), "r"(u.y) : "memory");
+}
+
+__device__ __forceinline__ void st_shadow4(__nv_bfloat16* shadow, size_t i, float4 v, uint32_t cols, uint32_t ld) {
+    if (cols == 0 || ((cols & 3u) == 0 && (ld & 3u) == 0)) {
+        st_shadow_bf16x4(shadow + shadow_index(i, cols, ld), v);       // the 4-pack stays inside one row
+    } else {
+        const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) shadow[shadow_index(i + k, cols, ld)] = __float2bfloat16(f[k]);
+    }
 }
 
 template <typename T>
@@ -224,14 +243,14 @@ tfy_ps_push_kernel(const TfyPsSeg* __restrict__ segs, float grad_scale, const fl
         }
         float4 neww;
         ps_apply4(opt, w + i * 4, s1 + i * 4, s2 + i * 4, gv, lr, eps, p1, p2, p3, shadow != nullptr, neww);
-        if (shadow) st_shadow_bf16x4(shadow + i * 4, neww);
+        if (shadow) st_shadow4(shadow, i * 4, neww, sg.cols, sg.shadow_ld);
     }
     if (blockIdx.x == 0) {   // scalar tail (n % 4 elements)
         for (size_t i = n4 * 4 + threadIdx.x; i < sg.n; i += blockDim.x) {
             float gv = (float)g[i] * grad_scale;
             if (wd != 0.f) gv += wd * w[i];
             const float nw = ps_apply1(opt, w + i, s1 + i, s2 + i, gv, lr, eps, p1, p2, p3);
-            if (shadow) shadow[i] = __float2bfloat16(nw);
+            if (shadow) shadow[shadow_index(i, sg.cols, sg.shadow_ld)] = __float2bfloat16(nw);
         }
     }
 }
@@ -287,7 +306,7 @@ template <typename GT>
 __global__ void __launch_bounds__(256)
 tfy_ps_push_rows_kernel(float* __restrict__ table, float* __restrict__ s1_table, float* __restrict__ s2_table,
                         const long long* __restrict__ ids, const GT* __restrict__ dout, int B, int L, int D, long long V,
-                        int mean, TfyPsHyper h, const float* __restrict__ adam_scale) {
+                        int mean, TfyPsHyper h, const float* __restrict__ adam_scale, int dout_ld) {
     const int D4 = D / 4;
     const size_t total = (size_t)B * L * D4;
     const float scale = (mean ? 1.f / (float)L : 1.f) * h.grad_scale;
@@ -298,7 +317,7 @@ tfy_ps_push_rows_kernel(float* __restrict__ table, float* __restrict__ s1_table,
         const int b = bj / L;
         const long long id = ids[bj];
         if (id < 0 || id >= V) continue;
-        const float4 gv = f4_mul(ld_local4<GT>(dout + (size_t)b * D + d), scale);
+        const float4 gv = f4_mul(ld_local4<GT>(dout + (size_t)b * dout_ld + d), scale);
         const size_t o = (size_t)id * D + d;
         float4 unused;
         ps_apply4(h.opt, table + o, s1_table + o, s2_table + o, gv, lr, h.eps, h.p1, h.p2, h.p3, false, unused);
@@ -309,7 +328,7 @@ template <typename GT>
 __global__ void __launch_bounds__(256)
 tfy_ps_push_rows_scalar_kernel(float* __restrict__ table, float* __restrict__ s1_table, float* __restrict__ s2_table,
                                const long long* __restrict__ ids, const GT* __restrict__ dout, int B, int L, int D,
-                               long long V, int mean, TfyPsHyper h, const float* __restrict__ adam_scale) {
+                               long long V, int mean, TfyPsHyper h, const float* __restrict__ adam_scale, int dout_ld) {
     const size_t total = (size_t)B * L * D;
     const float scale = (mean ? 1.f / (float)L : 1.f) * h.grad_scale;
     const float lr = (h.opt == TFY_OPT_ADAM && adam_scale) ? h.lr * adam_scale[0] : h.lr;
@@ -320,7 +339,7 @@ tfy_ps_push_rows_scalar_kernel(float* __restrict__ table, float* __restrict__ s1
         const long long id = ids[bj];
         if (id < 0 || id >= V) continue;
         const size_t o = (size_t)id * D + d;
-        ps_apply1(h.opt, table + o, s1_table + o, s2_table + o, (float)dout[(size_t)b * D + d] * scale, lr, h.eps, h.p1,
+        ps_apply1(h.opt, table + o, s1_table + o, s2_table + o, (float)dout[(size_t)b * dout_ld + d] * scale, lr, h.eps, h.p1,
                   h.p2, h.p3);
     }
 }
@@ -333,9 +352,10 @@ __global__ void __launch_bounds__(256) tfy_ps_refresh_shadow_kernel(const TfyPsS
     __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(sg.remote_shadow);
     const size_t n4 = sg.n / 4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
-        st_shadow_bf16x4(sh + i * 4, ld_peer_f32x4(w + i * 4));
+        st_shadow4(sh, i * 4, ld_peer_f32x4(w + i * 4), sg.cols, sg.shadow_ld);
     if (blockIdx.x == 0)
-        for (size_t i = n4 * 4 + threadIdx.x; i < sg.n; i += blockDim.x) sh[i] = __float2bfloat16(w[i]);
+        for (size_t i = n4 * 4 + threadIdx.x; i < sg.n; i += blockDim.x)
+            sh[shadow_index(i, sg.cols, sg.shadow_ld)] = __float2bfloat16(w[i]);
 }
 
 extern "C" {
@@ -402,7 +422,10 @@ int tfy_ps_embedding_bag(const void* table, const void* ids, void* out, int out_
 
 int tfy_ps_push_rows(void* table, void* s1_table, void* s2_table, const void* ids, const void* dout, int grad_is_bf16,
                      int B, int L, int D, long long V, int mean, int opt, float lr, float eps, float p1, float p2, float p3,
-                     float grad_scale, const float* adam_scale, cudaStream_t s) {
+                     float grad_scale, const float* adam_scale, int dout_ld, cudaStream_t s) {
+    // dout_ld: row pitch (elements) of dout; 0 = D (contiguous [B, D]).  A larger pitch lets the caller push a
+    // column slice of a wider gradient matrix (the fused first layer's dx) without copying it out.
+    if (dout_ld <= 0) dout_ld = D;
     if (opt != TFY_OPT_SGD && opt != TFY_OPT_ADAGRAD && opt != TFY_OPT_ADAM && opt != TFY_OPT_FTRL) return -3;
     if (opt != TFY_OPT_SGD && !s1_table) return -4;
     if ((opt == TFY_OPT_ADAM || opt == TFY_OPT_FTRL) && !s2_table) return -4;
@@ -418,21 +441,21 @@ int tfy_ps_push_rows(void* table, void* s1_table, void* s2_table, const void* id
         if (grad_is_bf16)
             tfy_ps_push_rows_scalar_kernel<__nv_bfloat16><<<(unsigned)g1, 256, 0, s>>>(
                 (float*)table, (float*)s1_table, (float*)s2_table, (const long long*)ids, (const __nv_bfloat16*)dout, B,
-                L, D, V, mean, h, adam_scale);
+                L, D, V, mean, h, adam_scale, dout_ld);
         else
             tfy_ps_push_rows_scalar_kernel<float><<<(unsigned)g1, 256, 0, s>>>(
                 (float*)table, (float*)s1_table, (float*)s2_table, (const long long*)ids, (const float*)dout, B, L, D, V,
-                mean, h, adam_scale);
+                mean, h, adam_scale, dout_ld);
         return (int)cudaGetLastError();
     }
     if (grad_is_bf16)
         tfy_ps_push_rows_kernel<__nv_bfloat16><<<(unsigned)gx, 256, 0, s>>>(
             (float*)table, (float*)s1_table, (float*)s2_table, (const long long*)ids, (const __nv_bfloat16*)dout, B, L, D,
-            V, mean, h, adam_scale);
+            V, mean, h, adam_scale, dout_ld);
     else
         tfy_ps_push_rows_kernel<float><<<(unsigned)gx, 256, 0, s>>>((float*)table, (float*)s1_table, (float*)s2_table,
                                                                     (const long long*)ids, (const float*)dout, B, L, D,
-                                                                    V, mean, h, adam_scale);
+                                                                    V, mean, h, adam_scale, dout_ld);
     return (int)cudaGetLastError();
 }
 

@@ -150,7 +150,16 @@ class SymmArena:
             native.check(self.lib.tfy_symm_exchange(self._h, tmo), "tfy_symm_exchange")
             self.rdv.barrier(f"{self._tag}/exchanged")
             trace("peers mapped; multicast setup")
-            if os.environ.get("TFY_DISABLE_NVLS") == "1":
+            # two ranks on ONE physical GPU (a ps sharing the chief's device on a small box) cannot both join a
+            # multicast object: fall back to plain peer mappings, which work within a device as well
+            try:
+                me = str(torch.cuda.get_device_properties(self.device).uuid)
+            except Exception:  # noqa: BLE001
+                me = f"dev{self.device}"
+            self.rdv.set(f"{self._tag}/dev/{self.rank}", me.encode())
+            devs = [self.rdv.get(f"{self._tag}/dev/{r}") for r in range(self.world)]
+            shared_device = len(set(devs)) < self.world
+            if os.environ.get("TFY_DISABLE_NVLS") == "1" or shared_device:
                 rc = 1
             else:
                 rc = self.lib.tfy_symm_mc_create(self._h, tmo)
