@@ -106,6 +106,8 @@ class BenchHook:
                     self.res["traffic"] = ps.traffic_per_step()
                 self.res["graph"] = bool(getattr(ctx.estimator, "_ps_graph", None) and
                                          "graph" in ctx.estimator._ps_graph)
+                self.res["graph_error"] = (getattr(ctx.estimator, "_ps_graph", None) or {}).get("error")
+                self.res["fused_first_layer"] = bool(getattr(ps, "fused_first", False))
                 me = os.environ.get("TFY_TASK_KEY", "chief:0").replace(":", "_")
                 with open(os.path.join(self.out_dir, f"bench_{me}.json"), "w") as f:
                     json.dump(self.res, f)
@@ -211,7 +213,9 @@ def run(args):
                                f"workers + {n_ps} ps", "global_batch": n_trainers * BATCH, "per_gpu_batch": BATCH,
                       "seq_len": None, "parallelism": f"async-ps {n_trainers} trainers / {n_ps} ps",
                       "l2": "embedding tables (26 x 100k x 64 fp32 x 3 slots = 2 GB) exceed the 126 MB L2",
-                      "cuda_graph": all(r.get("graph") for r in res), "launched_by": "run_on_yarn"},
+                      "cuda_graph": all(r.get("graph") for r in res), "graph_error": res[0].get("graph_error"),
+                      "k5_gather_fused_into_first_gemm": all(r.get("fused_first_layer") for r in res),
+                      "launched_by": "run_on_yarn"},
            "clocks": clocks,
            "e2e": {"value": n_trainers * BATCH * steps / (e2e_ms * 1e-3), "unit": "samples/s",
                    "h2d_bytes_per_step": BATCH * (N_NUM * 4 + N_CAT * 8 + 8), "d2h_bytes_per_step": 4, "steps": steps,

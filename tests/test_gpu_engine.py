@@ -329,7 +329,9 @@ def test_fused_dense_head_matches_autograd(B, K, C):
 
 
 @pytest.mark.parametrize("B,U,I,want_dx", [(128, 128, 9216, True), (128, 128, 9216, False), (64, 128, 1000, True),
-                                            (100, 72, 200, True), (16, 8, 64, True)])
+                                            (100, 72, 200, True), (16, 8, 64, True),
+                                            # batch / width beyond one tile: the tiled kernel (K loops, TMA ring)
+                                            (512, 1024, 1680, True), (300, 136, 264, True), (512, 256, 1024, False)])
 def test_tcgen05_dense_backward_matches_fp32_reference(B, U, I, want_dx):
     """dW = dh^T x and dx = dh W out of ONE tcgen05 kernel (MN-major operand views of the same tiles, TMA-store
     epilogue) vs fp32 matmuls of the same bf16 inputs; ragged extents exercise the TMA zero-fill / clipping."""

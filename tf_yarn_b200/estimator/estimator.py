@@ -376,15 +376,27 @@ class Estimator:
         captured in a CUDA graph and replayed on static input buffers: the data plane is a handful of
         microsecond-scale peer-memory kernels, so an eager step is bound by Python / launch overhead (the
         round-1 review measured it host-bound).  TFY_PS_GRAPH=0 keeps it eager."""
-        st = self._ps_graph
         if hasattr(self._ps, "refresh_adam_scale"):
             self._ps.refresh_adam_scale()
-        if st is None or st.get("off"):
-            loss = self._ps_step_body(features, labels)
-            if st is None:
-                st = self._ps_graph = {"warm": 0, "off": os.environ.get("TFY_PS_GRAPH", "1") == "0"}
+        st = self._ps_graph
+        if st is None:
+            st = self._ps_graph = {"warm": 0, "off": os.environ.get("TFY_PS_GRAPH", "1") == "0"}
+        if st["off"]:
+            return self._ps_step_body(features, labels)
+        if "graph" not in st:
+            prof_path = os.environ.get("TFY_PS_PROFILE")
+            if prof_path and st["warm"] == 2:
+                # per-kernel device times of ONE eager step (torch profiler / CUPTI), for tuning the data plane
+                from torch.profiler import ProfilerActivity, profile
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    loss = self._ps_step_body(features, labels)
+                    torch.cuda.synchronize()
+                with open(prof_path, "w") as f:
+                    f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+            else:
+                loss = self._ps_step_body(features, labels)      # eager warm-up steps
             st["warm"] += 1
-            if not st["off"] and st["warm"] == 3:
+            if st["warm"] >= 3:
                 try:
                     sf, sl = _clone_tensors(features), _clone_tensors(labels)
                     torch.cuda.synchronize()
@@ -396,8 +408,9 @@ class Estimator:
                 except Exception as exc:  # noqa: BLE001
                     logger.warning("CUDA-graph capture of the PS step failed (%s); staying eager", exc)
                     st["off"] = True
+                    st["error"] = f"{type(exc).__name__}: {exc}"[:600]
             return loss
-        if "graph" not in st or _signature(features, labels) != st["sig"]:
+        if _signature(features, labels) != st["sig"]:
             return self._ps_step_body(features, labels)          # odd-shaped batch: run it eagerly
         _copy_tensors(st["feats"], features)
         _copy_tensors(st["labels"], labels)

@@ -41,6 +41,9 @@ native.declare("tfy_dense_bwd", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
 native.declare("tfy_ps_embedding_bag", [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _vp])
 native.declare("tfy_ps_push_rows", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _i, _f, _f, _f, _f, _f, _f, _vp,
                                     _i, _vp])
+native.declare("tfy_ps_multi_bag", [_vp, _vp, _vp, _i, _i, _i, _i, _ll, _vp])
+native.declare("tfy_ps_multi_push_rows", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _i, _f, _f, _f, _f, _f, _f, _vp, _i,
+                                          _i, _vp])
 native.declare("tfy_ps_gather_gemm", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp])
 
 OPT_CODES = {"sgd": native.OPT_SGD, "adagrad": native.OPT_ADAGRAD, "adam": native.OPT_ADAM,
@@ -207,6 +210,7 @@ class HbmConnection:
         for idx, mod in self.gemm.items():
             mod.forward = _make_linear_forward(conn, idx, mod)
         self.fused_first = _try_fuse_first_layer(conn, network)
+        self.fused_wide = _try_fuse_wide_tower(conn, network)
 
     # ------------------------------------------------------------------ pull / push
     def pull(self, network: nn.Module) -> None:
@@ -361,6 +365,107 @@ def _make_linear_forward(conn: HbmConnection, idx: int, mod: nn.Linear):
     return forward
 
 
+class _TableGroup:
+    """T embedding tables of one tower served by the multi-table kernels (one launch for the whole group)."""
+
+    def __init__(self, conn: HbmConnection, tables_idx: List[int], cat_cols):
+        lay = conn.layout
+        self.conn, self.idx, self.cols = conn, tables_idx, cat_cols
+        first = tables_idx[0]
+        self.uniform = all(lay.kinds[i] == lay.kinds[first] and lay.hypers[i] == lay.hypers[first] for i in tables_idx)
+        dev = conn.device
+        self.tables = torch.tensor([conn.master_ptr(i) for i in tables_idx], dtype=torch.int64, device=dev)
+        ns = lay.var_slots[first]
+        self.s1 = torch.tensor([conn.master_ptr(i, 1) for i in tables_idx], dtype=torch.int64, device=dev) if ns >= 1 else None
+        self.s2 = torch.tensor([conn.master_ptr(i, 2) for i in tables_idx], dtype=torch.int64, device=dev) if ns >= 2 else None
+        self.V = cat_cols[0].num_buckets
+        self.same_v = all(c.num_buckets == self.V and c.hashed == cat_cols[0].hashed for c in cat_cols)
+        h = lay.hypers[first]
+        self.h = h
+        self.opt = conn.var_opt[first]
+        self.p3 = float(h["eps"]) if lay.kinds[first] == "ftrl" else 0.0
+        self.slots = ns
+
+    def ids_of(self, features) -> torch.Tensor:
+        """int64 [T, B] bucket ids of the batch: ONE hash over the stacked columns (26 separate 3-kernel hashes
+        were 40 % of the step's device time in the first profile)."""
+        raw = torch.stack([features[c.key].reshape(-1) for c in self.cols]).long()
+        if self.cols[0].hashed:
+            raw = (raw * 2654435761) % (2 ** 32)
+        return (raw % self.V).contiguous()
+
+    def push(self, ids: torch.Tensor, dout: torch.Tensor, D: int, dout_ld: int, col_stride: int) -> None:
+        conn, h = self.conn, self.h
+        B, T = ids.shape[1], len(self.idx)
+        native.check(conn.lib.tfy_ps_multi_push_rows(
+            self.tables.data_ptr(), self.s1.data_ptr() if self.s1 is not None else None,
+            self.s2.data_ptr() if self.s2 is not None else None, ids.data_ptr(), dout.data_ptr(),
+            1 if dout.dtype == torch.bfloat16 else 0, B, T, D, self.V, self.opt, float(h["lr"]), float(h["eps"]),
+            float(h["p1"]), float(h["p2"]), self.p3, 1.0, conn.adam_scale.data_ptr(), dout_ld, col_stride,
+            torch.cuda.current_stream().cuda_stream), "tfy_ps_multi_push_rows")
+        conn.account(push=T * B * D * 4 * (1 + self.slots))
+
+
+def _try_fuse_wide_tower(conn: HbmConnection, network: nn.Module) -> bool:
+    """The wide tower (fc.LinearModel): T per-bucket weight tables [V, units] looked up once per example and summed.
+    One multi-table gather kernel forward, one multi-table push (FTRL / ... fused) backward, instead of T launches
+    each plus T adds."""
+    from tf_yarn_b200.estimator import feature_column as fc
+    if os.environ.get("TFY_PS_FUSE_WIDE", "1") == "0":
+        return False
+    lin = getattr(network, "linear", None)
+    if not isinstance(lin, fc.LinearModel) or not lin.tables:
+        return False
+    by_param = {id(p): i for i, p in enumerate(conn.params)}
+    cat_cols, tables_idx = [], []
+    for c in lin.columns:
+        cc = c.categorical_column if isinstance(c, (fc.EmbeddingColumn, fc.IndicatorColumn)) else c
+        if isinstance(cc, fc.CategoricalColumn):
+            emb = lin.tables[cc.key]
+            ti = by_param.get(id(emb.weight))
+            if ti is None or ti not in conn.sparse or emb.mode != "sum":
+                return False
+            cat_cols.append(cc)
+            tables_idx.append(ti)
+    group = _TableGroup(conn, tables_idx, cat_cols)
+    if not (group.uniform and group.same_v):
+        return False
+    units = lin.units
+    dev = conn.device
+
+    class _MultiBag(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, ids, anchor):
+            B = ids.shape[1]
+            out = torch.empty((B, units), dtype=torch.float32, device=dev)
+            native.check(conn.lib.tfy_ps_multi_bag(group.tables.data_ptr(), ids.data_ptr(), out.data_ptr(), 0, B,
+                                                   len(tables_idx), units, group.V,
+                                                   torch.cuda.current_stream().cuda_stream), "tfy_ps_multi_bag")
+            conn.account(pull=B * len(tables_idx) * units * 4)
+            ctx.ids = ids
+            return out
+
+        @staticmethod
+        def backward(ctx, dout):
+            group.push(ctx.ids, dout.contiguous().float(), units, units, 0)     # every table gets the same gradient
+            return None, None
+
+    anchor = torch.zeros((), device=dev, requires_grad=True)
+    num_cols = [c for c in lin.columns if isinstance(c, fc.NumericColumn)]
+
+    def forward(features):
+        out = _MultiBag.apply(group.ids_of(features), anchor)
+        if lin.numeric is not None and num_cols:
+            nums = [features[c.key].reshape(features[c.key].shape[0], -1).float() for c in num_cols]
+            x = nums[0] if len(nums) == 1 else torch.cat(nums, dim=1)
+            out = out + lin.numeric(x.to(lin.numeric.weight.dtype))
+        return out + lin.bias
+
+    lin.forward = forward
+    logger.info("wide tower: %d tables served by the multi-table gather / push kernels", len(tables_idx))
+    return True
+
+
 def _try_fuse_first_layer(conn: HbmConnection, network: nn.Module) -> bool:
     """K5: fuse the sparse pull of the embedding rows INTO the first deep GEMM (ops/csrc/tfy_ps_gemm.cu).
 
@@ -405,7 +510,8 @@ def _try_fuse_first_layer(conn: HbmConnection, network: nn.Module) -> bool:
     dev = conn.device
     N, K, Kp = lin.out_features, lin.in_features, conn.shadow_ld(widx)
     shadow = conn.shadow_ptr(widx)
-    table_ptrs = torch.tensor([conn.master_ptr(ti) for ti in tables_idx], dtype=torch.int64, device=dev)
+    group = _TableGroup(conn, tables_idx, [c.categorical_column for c in emb_cols])
+    table_ptrs = group.tables
     lib, lay = conn.lib, conn.layout
 
     class _FusedFirst(torch.autograd.Function):
@@ -434,7 +540,11 @@ def _try_fuse_first_layer(conn: HbmConnection, network: nn.Module) -> bool:
             native.check(lib.tfy_dense_bwd(dyb.data_ptr(), xbuf.data_ptr(), shadow, dw.data_ptr(), dx.data_ptr(), B, N,
                                            Kp, s), "tfy_dense_bwd")
             conn.account(pull=N * Kp * 2)
-            for t, ti in enumerate(tables_idx):          # sparse push of table t from columns [64 t, 64 t + 64) of dx
+            if group.uniform:
+                # table t takes columns [64 t, 64 t + 64) of dx: ONE launch for all tables, straight out of dx
+                group.push(ids, dx, 64, Kp, 64)
+                return None, None, dw[:, :K].to(weight.dtype), dy.float().sum(0).to(weight.dtype)
+            for t, ti in enumerate(tables_idx):          # (mixed optimizers) table by table
                 h = lay.hypers[ti]
                 s1 = conn.master_ptr(ti, 1) if lay.var_slots[ti] >= 1 else None
                 s2 = conn.master_ptr(ti, 2) if lay.var_slots[ti] >= 2 else None
@@ -456,8 +566,11 @@ def _try_fuse_first_layer(conn: HbmConnection, network: nn.Module) -> bool:
             return self
 
     def df_forward(features):
-        ids = torch.stack([fc._ids(c.categorical_column, features[c.categorical_column.key]).reshape(-1)
-                           for c in emb_cols]).contiguous()
+        if group.same_v:
+            ids = group.ids_of(features)
+        else:
+            ids = torch.stack([fc._ids(c.categorical_column, features[c.categorical_column.key]).reshape(-1)
+                               for c in emb_cols]).contiguous()
         numeric = None
         if num_cols:
             parts = [features[c.key].reshape(features[c.key].shape[0], -1).float() for c in num_cols]

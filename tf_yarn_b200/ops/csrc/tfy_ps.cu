@@ -344,6 +344,66 @@ tfy_ps_push_rows_scalar_kernel(float* __restrict__ table, float* __restrict__ s1
     }
 }
 
+// ------------------------------------------------------------------------------- multi-table sparse ops
+// A wide-and-deep step touches one row in each of T tables per example (26 hashed categorical columns, twice: the
+// wide tower's [V, 1] tables and the deep tower's [V, 64] tables).  One launch per table made the step launch-bound
+// (52 gathers + 52 pushes + 26 adds of ~3 us each, profiles/r2/ps_step_profile_r2q.txt); these kernels take the
+// whole group: tables = device array of T peer pointers, ids = int64 [T, B].
+//   multi_bag      : out[b, d] = sum_t table_t[ids[t, b], d]                      (the wide tower's logit)
+//   multi_push_rows: row ids[t, b] of table t receives dout[b, t * col_stride + d] (col_stride 0: every table gets
+//                    the same gradient -- wide tower; col_stride D: column slices of a wider matrix -- the fused
+//                    first deep layer's dx), optimizer fused as in tfy_ps_push_rows.
+template <typename OT>
+__global__ void __launch_bounds__(256)
+tfy_ps_multi_bag_kernel(const uint64_t* __restrict__ tables, const long long* __restrict__ ids, OT* __restrict__ out,
+                        int B, int T, int D, long long V) {
+    const size_t total = (size_t)B * D;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = i / D, d = i % D;
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const long long id = ids[(size_t)t * B + b];
+            if (id < 0 || id >= V) continue;
+            float v;
+            asm volatile("ld.global.relaxed.sys.L1::no_allocate.f32 %0, [%1];"
+                         : "=f"(v)
+                         : "l"(reinterpret_cast<const float*>(tables[t]) + (size_t)id * D + d)
+                         : "memory");
+            acc += v;
+        }
+        out[i] = (OT)acc;
+    }
+}
+
+template <typename GT, int VEC>
+__global__ void __launch_bounds__(256)
+tfy_ps_multi_push_rows_kernel(const uint64_t* __restrict__ tables, const uint64_t* __restrict__ s1s,
+                              const uint64_t* __restrict__ s2s, const long long* __restrict__ ids,
+                              const GT* __restrict__ dout, int B, int T, int D, long long V, TfyPsHyper h,
+                              const float* __restrict__ adam_scale, int dout_ld, int col_stride) {
+    const int DV = D / VEC;
+    const size_t total = (size_t)T * B * DV;
+    const float lr = (h.opt == TFY_OPT_ADAM && adam_scale) ? h.lr * adam_scale[0] : h.lr;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int d = (i % DV) * VEC;
+        const size_t tb = i / DV;
+        const int b = tb % B, t = tb / B;
+        const long long id = ids[tb];
+        if (id < 0 || id >= V) continue;
+        const size_t o = (size_t)id * D + d;
+        float* w = reinterpret_cast<float*>(tables[t]) + o;
+        float* s1 = s1s ? reinterpret_cast<float*>(s1s[t]) + o : nullptr;
+        float* s2 = s2s ? reinterpret_cast<float*>(s2s[t]) + o : nullptr;
+        const GT* g = dout + (size_t)b * dout_ld + (size_t)t * col_stride + d;
+        if (VEC == 4) {
+            float4 unused;
+            ps_apply4(h.opt, w, s1, s2, f4_mul(ld_local4<GT>(g), h.grad_scale), lr, h.eps, h.p1, h.p2, h.p3, false, unused);
+        } else {
+            ps_apply1(h.opt, w, s1, s2, (float)g[0] * h.grad_scale, lr, h.eps, h.p1, h.p2, h.p3);
+        }
+    }
+}
+
 // fp32 -> bf16 shadow refresh of a whole segment (run by the chief after initialisation / restore)
 __global__ void __launch_bounds__(256) tfy_ps_refresh_shadow_kernel(const TfyPsSeg* __restrict__ segs) {
     const TfyPsSeg sg = segs[blockIdx.y];
@@ -456,6 +516,44 @@ int tfy_ps_push_rows(void* table, void* s1_table, void* s2_table, const void* id
         tfy_ps_push_rows_kernel<float><<<(unsigned)gx, 256, 0, s>>>((float*)table, (float*)s1_table, (float*)s2_table,
                                                                     (const long long*)ids, (const float*)dout, B, L, D,
                                                                     V, mean, h, adam_scale, dout_ld);
+    return (int)cudaGetLastError();
+}
+
+int tfy_ps_multi_bag(const uint64_t* tables, const void* ids, void* out, int out_is_bf16, int B, int T, int D,
+                     long long V, cudaStream_t s) {
+    if (B < 1 || T < 1 || D < 1) return -2;
+    size_t gx = ((size_t)B * D + 255) / 256;
+    if (gx > 148 * 8) gx = 148 * 8;
+    if (out_is_bf16)
+        tfy_ps_multi_bag_kernel<__nv_bfloat16><<<(unsigned)gx, 256, 0, s>>>(tables, (const long long*)ids,
+                                                                           (__nv_bfloat16*)out, B, T, D, V);
+    else
+        tfy_ps_multi_bag_kernel<float><<<(unsigned)gx, 256, 0, s>>>(tables, (const long long*)ids, (float*)out, B, T, D, V);
+    return (int)cudaGetLastError();
+}
+
+// s1s / s2s: device arrays of T slot-table pointers (nullptr when the optimizer has no such slot)
+int tfy_ps_multi_push_rows(const uint64_t* tables, const uint64_t* s1s, const uint64_t* s2s, const void* ids,
+                           const void* dout, int grad_is_bf16, int B, int T, int D, long long V, int opt, float lr,
+                           float eps, float p1, float p2, float p3, float grad_scale, const float* adam_scale,
+                           int dout_ld, int col_stride, cudaStream_t s) {
+    if (opt != TFY_OPT_SGD && opt != TFY_OPT_ADAGRAD && opt != TFY_OPT_ADAM && opt != TFY_OPT_FTRL) return -3;
+    if (opt != TFY_OPT_SGD && !s1s) return -4;
+    if ((opt == TFY_OPT_ADAM || opt == TFY_OPT_FTRL) && !s2s) return -4;
+    if (dout_ld <= 0) dout_ld = D;
+    TfyPsHyper h;
+    h.opt = opt; h.lr = lr; h.eps = eps; h.wd = 0.f; h.p1 = p1; h.p2 = p2; h.p3 = p3; h.grad_scale = grad_scale;
+    const bool vec = (D % 4 == 0) && (dout_ld % 4 == 0) && (col_stride % 4 == 0);
+    size_t gx = ((size_t)T * B * (vec ? D / 4 : D) + 255) / 256;
+    if (gx < 1) gx = 1;
+    if (gx > 148 * 8) gx = 148 * 8;
+#define TFY_MPR(GT, VV)                                                                                              \
+    tfy_ps_multi_push_rows_kernel<GT, VV><<<(unsigned)gx, 256, 0, s>>>(tables, s1s, s2s, (const long long*)ids,       \
+                                                                       (const GT*)dout, B, T, D, V, h, adam_scale,    \
+                                                                       dout_ld, col_stride)
+    if (grad_is_bf16) { if (vec) TFY_MPR(__nv_bfloat16, 4); else TFY_MPR(__nv_bfloat16, 1); }
+    else { if (vec) TFY_MPR(float, 4); else TFY_MPR(float, 1); }
+#undef TFY_MPR
     return (int)cudaGetLastError();
 }
 

@@ -176,24 +176,35 @@ tfy_ps_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const uint6
         const int r = (warp - 2) * 32 + lane;
         const int b = b0 + r;
         const bool live = b < B;
+        // The row of chunk c + 1 is requested BEFORE chunk c is converted and published (two rows = 128 registers
+        // in flight per thread): a gather is one NVLink/HBM round trip per chunk, and with one row in flight the 27
+        // round trips of the K loop were serialised (104 us for 512 x 1680 x 1024, r2q profile).
+        auto row_of = [&](int c) -> const float* {
+            if (!live || c >= T) return nullptr;
+            const long long id = ids[(size_t)c * B + b];
+            return (id >= 0 && id < V) ? reinterpret_cast<const float*>(tables[c]) + (size_t)id * 64 : nullptr;
+        };
+        float4 cur[16], nxt[16];
+        {
+            const float* row = row_of(0);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) cur[q] = row ? pg_ld_peer(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int c = 0; c < n_chunks; ++c) {
             const int s = c % PG_STAGES;
+            if (c + 1 < T) {
+                const float* row = row_of(c + 1);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) nxt[q] = row ? pg_ld_peer(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             uint4 packs[8];
             if (c < T) {
-                const float* row = nullptr;
-                if (live) {
-                    const long long id = ids[(size_t)c * B + b];
-                    if (id >= 0 && id < V) row = reinterpret_cast<const float*>(tables[c]) + (size_t)id * 64;
-                }
-                float4 v[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = row ? pg_ld_peer(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    packs[q].x = tfy_pack_bf16x2(v[2 * q].x, v[2 * q].y);
-                    packs[q].y = tfy_pack_bf16x2(v[2 * q].z, v[2 * q].w);
-                    packs[q].z = tfy_pack_bf16x2(v[2 * q + 1].x, v[2 * q + 1].y);
-                    packs[q].w = tfy_pack_bf16x2(v[2 * q + 1].z, v[2 * q + 1].w);
+                    packs[q].x = tfy_pack_bf16x2(cur[2 * q].x, cur[2 * q].y);
+                    packs[q].y = tfy_pack_bf16x2(cur[2 * q].z, cur[2 * q].w);
+                    packs[q].z = tfy_pack_bf16x2(cur[2 * q + 1].x, cur[2 * q + 1].y);
+                    packs[q].w = tfy_pack_bf16x2(cur[2 * q + 1].z, cur[2 * q + 1].w);
                 }
             } else {
                 float f[64];
@@ -214,6 +225,8 @@ tfy_ps_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const uint6
                 for (int q = 0; q < 8; ++q)
                     if (c * 64 + q * 8 + 8 <= Kp) tfy_st16(xr + q * 8, packs[q]);
             }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) cur[q] = nxt[q];
         }
         // ===== epilogue: bias, bf16, row-contiguous 16-byte stores =====
         const int quad = warp & 3;
