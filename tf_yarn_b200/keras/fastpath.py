@@ -15,7 +15,7 @@ the step does not go through autograd at all:
 * weight gradients are written straight into the flat gradient buffer consumed by the fused
   reduce-scatter / optimizer / all-gather kernel (no ``grad += g`` accumulation launches).
 
-10 launches per MNIST-CNN step, all of them our kernels (no cuBLAS / cuDNN), against 53 for the autograd engine
+9 launches per MNIST-CNN step, all of them our kernels (no cuBLAS / cuDNN), against 53 for the autograd engine
 (profiles/launches_*.csv).  Layers or shapes outside the kernels' envelope fall back to cuDNN / cuBLAS +
 the element-wise fused kernels of ``tfy_nn.cu``; models outside the grammar use the autograd engine
 (:class:`GraphTrainEngine`).
@@ -54,6 +54,8 @@ native.declare("tfy_conv3x3_c32_wgrad_unpool", [_vp, _vp, _vp, _f, _vp, _vp, _vp
 native.declare("tfy_conv3x3_c32_wgrad_unpool_ov", [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp])
 native.declare("tfy_conv3x3_c32_wgrad_spare_ctas", [_i, _i, _i])
 native.declare("tfy_dense_bwd", [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp])
+native.declare("tfy_gemm_bf16_splitk_fused", [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _u32, _vp, _i,
+                                              _vp])
 native.declare("tfy_dense_head_scratch_elems", [_i, _i], restype=ctypes.c_size_t)
 native.declare("tfy_dense_head_fused", [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
                                         _i, _vp])
@@ -382,14 +384,27 @@ class FastSequentialEngine(GraphTrainEngine):
                     # skinny GEMM with a long K (e.g. 128 x 128 x 9216): split K over ~48 CTAs of the
                     # tcgen05 kernel; partial sums meet in an fp32 accumulator that the epilogue clears
                     acc = self._splitk_acc(li, B, ly.units)
-                    self._chk(lib.tfy_gemm_bf16(xin.data_ptr(), w.data_ptr(), None, acc.data_ptr(), None, B,
-                                                ly.units, K, xin.stride(0), w.stride(0), ly.units, 0, split, s),
-                              "gemm_bf16(split-K)")
                     z = torch.empty((B, ly.units), dtype=bf16, device=cur.device)
-                    self._chk(lib.tfy_bias_act_drop_fwd_f32(acc.data_ptr(), b.data_ptr(), z.data_ptr(),
-                                                            mask.data_ptr() if mask is not None else None, B,
-                                                            ly.units, int(st.relu), float(st.drop), seed, self._hp,
-                                                            s), "bias_act_drop_fwd_f32")
+                    if os.environ.get("TFY_NO_SPLITK_FUSE") != "1":
+                        # ONE launch: the CTA that completes a tile applies bias + ReLU + dropout, writes the bf16
+                        # activations and the gate mask and clears the accumulator (last-arriver epilogue)
+                        key = ("splitk_cnt", li)
+                        if key not in self._acc32:
+                            tiles = ((B + 127) // 128) * ((ly.units + 127) // 128)
+                            self._acc32[key] = torch.zeros(tiles, dtype=torch.int32, device=cur.device)
+                        self._chk(lib.tfy_gemm_bf16_splitk_fused(
+                            xin.data_ptr(), w.data_ptr(), acc.data_ptr(), self._acc32[key].data_ptr(), b.data_ptr(),
+                            z.data_ptr(), mask.data_ptr() if mask is not None else None, B, ly.units, K,
+                            xin.stride(0), w.stride(0), int(st.relu), float(st.drop), seed, self._hp, split, s),
+                            "gemm_bf16_splitk_fused")
+                    else:
+                        self._chk(lib.tfy_gemm_bf16(xin.data_ptr(), w.data_ptr(), None, acc.data_ptr(), None, B,
+                                                    ly.units, K, xin.stride(0), w.stride(0), ly.units, 0, split, s),
+                                  "gemm_bf16(split-K)")
+                        self._chk(lib.tfy_bias_act_drop_fwd_f32(acc.data_ptr(), b.data_ptr(), z.data_ptr(),
+                                                                mask.data_ptr() if mask is not None else None, B,
+                                                                ly.units, int(st.relu), float(st.drop), seed, self._hp,
+                                                                s), "bias_act_drop_fwd_f32")
                 else:
                     z = torch.mm(xin, w.t())
                     self._chk(lib.tfy_bias_act_drop_fwd(z.data_ptr(), b.data_ptr(), z.data_ptr(),

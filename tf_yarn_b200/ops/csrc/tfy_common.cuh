@@ -226,6 +226,19 @@ __device__ __forceinline__ uint32_t tfy_pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Counter-based dropout randomness shared by every kernel that draws a mask: hash(seed, layer salt, optimizer step,
+// element); the step is read from the device-resident TfyOptHyper, so a replayed CUDA graph draws fresh masks.
+__device__ __forceinline__ uint32_t tfy_hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+// uniform in [0,1) for (seed, step, index)
+__device__ __forceinline__ float tfy_uniform(uint32_t seed, uint32_t step, uint64_t idx) {
+    uint32_t h = tfy_hash32(seed ^ tfy_hash32(step * 0x9E3779B9U + 0x85ebca6bU) ^
+                            tfy_hash32((uint32_t)idx * 0xC2B2AE35U + (uint32_t)(idx >> 32) + 0x27d4eb2fU));
+    return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
 template <typename T>
 struct TfyPack;  // 16-byte pack of T
 

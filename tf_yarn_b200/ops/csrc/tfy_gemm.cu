@@ -107,11 +107,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 
 }  // namespace
 
+// Fused split-K epilogue (out_mode 2): what runs after the partial sums of ALL K-slices of a tile have been added.
+// The CTA whose arrival completes the tile reads the fp32 accumulator back (L2), clears it for the next step,
+// applies bias + ReLU + dropout and writes the bf16 activations and the gradient-gate mask -- the work of the
+// separate tfy_bias_act_drop_fwd_f32 launch of round 1 (same element indexing, same random numbers).
+struct TfySplitKEpilogue {
+    uint32_t* counters;      // one per output tile, zero on entry, left zero
+    __nv_bfloat16* y;        // [M, N] bf16 activations (row pitch ldy)
+    uint8_t* mask;           // [M, N] bytes: 1 = gradient flows (optional)
+    const TfyOptHyper* hp;   // dropout step counter
+    float drop_rate;
+    uint32_t seed;
+    int ldy;
+};
+
 // out_mode 0: C (bf16) = act(acc + bias)      out_mode 1: C32 (fp32) += acc   (split-K partial sums)
+// out_mode 2: as 1, then the last-arriving CTA of every tile runs the fused epilogue above
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      __nv_bfloat16* __restrict__ C, float* __restrict__ C32, const __nv_bfloat16* __restrict__ bias,
-                     int M, int N, int K, int ldc, int relu, int out_mode, int k_tiles_per_split) {
+                     int M, int N, int K, int ldc, int relu, int out_mode, int k_tiles_per_split, TfySplitKEpilogue ep) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
@@ -201,7 +216,7 @@ tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             float v[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-            if (out_mode == 1) {
+            if (out_mode >= 1) {
                 float* dst = C32 + (size_t)row * ldc + n;
                 if (n + 16 <= N && (ldc & 3) == 0 && (n & 3) == 0) {
                     // 4 x red.v4.f32 instead of 16 scalar REDs
@@ -234,6 +249,59 @@ tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                     for (int j = 0; j < 16; ++j)
                         if (n + j < N) dst[j] = __float2bfloat16(v[j]);
                 }
+            }
+        }
+    }
+    if (out_mode == 2 && warp >= 2) {
+        // ---- fused split-K epilogue: the four epilogue warps of the CTA that completes the tile ----
+        __shared__ uint32_t s_last;
+        asm volatile("bar.sync 1, 128;" ::: "memory");                 // this CTA's red.adds are all issued
+        if (threadIdx.x == 64) {
+            __threadfence();
+            uint32_t* cnt = ep.counters + blockIdx.y * gridDim.x + blockIdx.x;
+            const uint32_t prev = atomicAdd(cnt, 1u);
+            s_last = (prev == gridDim.z - 1) ? 1u : 0u;
+            if (s_last) *cnt = 0u;                                     // re-armed for the next launch / graph replay
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (s_last) {
+            __threadfence();
+            const uint32_t step = ep.hp ? (uint32_t)ep.hp->step : 0u;
+            const float keep_scale = ep.drop_rate > 0.f ? 1.f / (1.f - ep.drop_rate) : 1.f;
+            const int t = threadIdx.x - 64;                            // 0..127
+            const int G = N / 8;                                       // 8-element groups per row (N % 8 == 0)
+            const int tile_g = BN / 8;
+            for (int i = t; i < BM * tile_g; i += 128) {
+                const int r = i / tile_g, gq = i % tile_g;
+                const int row = m0 + r, n = n0 + gq * 8;
+                if (row >= M || n >= N) continue;
+                float4* zp = reinterpret_cast<float4*>(C32 + (size_t)row * ldc + n);
+                const float4 a = __ldcg(zp), b = __ldcg(zp + 1);
+                zp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                zp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                if (bias) {
+                    float bv[8];
+                    TfyPack<__nv_bfloat16>::unpack(tfy_ld16(bias + n), bv);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] += bv[k];
+                }
+                const size_t idx = (size_t)row * G + n / 8;            // group index of the un-fused kernel
+                uint32_t m_lo = 0, m_hi = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    bool on = true;
+                    if (relu) { on = v[k] > 0.f; v[k] = on ? v[k] : 0.f; }
+                    if (ep.drop_rate > 0.f) {
+                        const bool keep = tfy_uniform(ep.seed, step, idx * 8 + k) >= ep.drop_rate;
+                        v[k] = keep ? v[k] * keep_scale : 0.f;
+                        on = on && keep;
+                    }
+                    if (k < 4) m_lo |= (on ? 1u : 0u) << (8 * k);
+                    else m_hi |= (on ? 1u : 0u) << (8 * (k - 4));
+                }
+                tfy_st16(ep.y + (size_t)row * ep.ldy + n, TfyPack<__nv_bfloat16>::pack(v));
+                if (ep.mask) *reinterpret_cast<uint2*>(ep.mask + (size_t)row * N + n) = make_uint2(m_lo, m_hi);
             }
         }
     }
@@ -308,7 +376,38 @@ int tfy_gemm_bf16(const void* A, const void* B, void* C, float* C32, const void*
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, split_k);
     tfy_launch_pdl((tfy_gemm_bf16_kernel), dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, s, ma, mb, (__nv_bfloat16*)C, C32,
                                                                 (const __nv_bfloat16*)bias, M, N, K, ldc, relu,
-                                                                out_mode, per);
+                                                                out_mode, per, TfySplitKEpilogue{});
+    return (int)cudaGetLastError();
+}
+
+// Split-K GEMM with the fused epilogue: y[M,N] (bf16) = dropout(act(A . B^T + bias)), mask[M,N] (optional bytes).
+// acc32 [M,N] fp32 (row pitch N) is scratch that must be zero on entry and is left zero; counters: one uint32 per
+// 128x128 output tile, zero on entry, left zero.  N % 8 == 0.
+int tfy_gemm_bf16_splitk_fused(const void* A, const void* B, float* acc32, uint32_t* counters, const void* bias, void* y,
+                               void* mask, int M, int N, int K, int lda, int ldb, int relu, float drop_rate, uint32_t seed,
+                               const TfyOptHyper* hp, int split_k, cudaStream_t s) {
+    if ((K & 7) || (lda & 7) || (ldb & 7) || (N & 7)) return -2;
+    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)y & 15)) return -3;
+    if (!load_encode()) return -4;
+    if (!g_attr_set) {
+        if (cudaFuncSetAttribute(tfy_gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
+            cudaSuccess)
+            return -5;
+        g_attr_set = true;
+    }
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, A, M, K, lda) || !make_map(&mb, B, N, K, ldb)) return -6;
+    const int k_tiles = (K + BK - 1) / BK;
+    if (split_k < 1) split_k = 1;
+    if (split_k > k_tiles) split_k = k_tiles;
+    const int per = (k_tiles + split_k - 1) / split_k;
+    split_k = (k_tiles + per - 1) / per;
+    TfySplitKEpilogue ep;
+    ep.counters = counters; ep.y = (__nv_bfloat16*)y; ep.mask = (uint8_t*)mask; ep.hp = hp;
+    ep.drop_rate = drop_rate; ep.seed = seed; ep.ldy = N;
+    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, split_k);
+    tfy_launch_pdl((tfy_gemm_bf16_kernel), dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, s, ma, mb, (__nv_bfloat16*)nullptr,
+                   acc32, (const __nv_bfloat16*)bias, M, N, K, N, relu, 2, per, ep);
     return (int)cudaGetLastError();
 }
 

@@ -22,17 +22,6 @@
 
 namespace {
 
-__device__ __forceinline__ uint32_t tfy_hash32(uint32_t x) {
-    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-    return x;
-}
-// uniform in [0,1) for (seed, step, index)
-__device__ __forceinline__ float tfy_uniform(uint32_t seed, uint32_t step, uint64_t idx) {
-    uint32_t h = tfy_hash32(seed ^ tfy_hash32(step * 0x9E3779B9U + 0x85ebca6bU) ^
-                            tfy_hash32((uint32_t)idx * 0xC2B2AE35U + (uint32_t)(idx >> 32) + 0x27d4eb2fU));
-    return (float)(h >> 8) * (1.0f / 16777216.0f);
-}
-
 __device__ __forceinline__ float bf16_to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // Cross-CTA column sums without a serial tail: every CTA adds its C block sums (in shared memory)

@@ -14,7 +14,9 @@
 //   * tcgen05.mma M128 N256 K16 accumulates in TMEM; the epilogue adds the bias and stores bf16.
 // The gathered activations are also written out once (bf16, [B, Kp]) because the backward needs them
 // (dW = dy^T x, tfy_dense_bwd).  K chunk c < T is table c (embedding dim 64); chunk T holds the numeric features.
-// warp 0: TMA (B tiles)   warp 1: TMEM + MMA issue   warps 2-5: A-tile producers, then the epilogue
+// warp 0: TMA (B tiles)   warp 1: TMEM + MMA issue   warps 2-17: A-tile producers (4 threads per row, 3 chunks in
+// flight each: a gather is a dependent id -> row round trip to (remote) HBM per chunk, so the K loop is only as
+// fast as the number of rows in flight)   warps 2-5 then run the epilogue
 #include <cuda.h>
 
 #include "tfy_common.cuh"
@@ -23,7 +25,9 @@ namespace {
 
 constexpr int PG_BM = 128, PG_BN = 256, PG_BK = 64, PG_STAGES = 4;
 constexpr int PG_A_BYTES = PG_BM * PG_BK * 2, PG_B_BYTES = PG_BN * PG_BK * 2, PG_STAGE_BYTES = PG_A_BYTES + PG_B_BYTES;
-constexpr int PG_THREADS = 192;
+constexpr int PG_PROD_WARPS = 16, PG_PROD_THREADS = PG_PROD_WARPS * 32;   // 4 threads per A-tile row
+constexpr int PG_DEPTH = 3;                                                  // gathered chunks in flight per thread
+constexpr int PG_THREADS = (2 + PG_PROD_WARPS) * 32;                         // 576
 constexpr size_t PG_SMEM = 1024 + (size_t)PG_STAGES * PG_STAGE_BYTES + 512;
 
 __device__ __forceinline__ uint32_t pg_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,7 +125,7 @@ tfy_ps_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const uint6
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
         for (int s = 0; s < PG_STAGES; ++s) {
-            pg_mbar_init(&full_a[s], 128);      // the 128 producer threads
+            pg_mbar_init(&full_a[s], PG_PROD_THREADS);
             pg_mbar_init(&full_b[s], 1);
             pg_mbar_init(&empty[s], 1);
         }
@@ -172,62 +176,64 @@ tfy_ps_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const uint6
             pg_commit(acc_full);
         }
     } else {
-        // ===== A-tile producers: thread r gathers sample b0 + r; chunk c = table c (or the numeric features) =====
-        const int r = (warp - 2) * 32 + lane;
+        // ===== A-tile producers: 4 threads per sample; thread (r, p) owns columns [16 p, 16 p + 16) of every chunk =====
+        const int pt = (int)threadIdx.x - 64;
+        const int r = pt >> 2, p = pt & 3;
         const int b = b0 + r;
         const bool live = b < B;
-        // The row of chunk c + 1 is requested BEFORE chunk c is converted and published (two rows = 128 registers
-        // in flight per thread): a gather is one NVLink/HBM round trip per chunk, and with one row in flight the 27
-        // round trips of the K loop were serialised (104 us for 512 x 1680 x 1024, r2q profile).
-        auto row_of = [&](int c) -> const float* {
-            if (!live || c >= T) return nullptr;
-            const long long id = ids[(size_t)c * B + b];
-            return (id >= 0 && id < V) ? reinterpret_cast<const float*>(tables[c]) + (size_t)id * 64 : nullptr;
+        auto issue = [&](int c, float4* dst) {
+            const float* row = nullptr;
+            if (live && c < T) {
+                const long long id = ids[(size_t)c * B + b];
+                if (id >= 0 && id < V) row = reinterpret_cast<const float*>(tables[c]) + (size_t)id * 64 + p * 16;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = row ? pg_ld_peer(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        float4 cur[16], nxt[16];
-        {
-            const float* row = row_of(0);
+        float4 buf[PG_DEPTH][4];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) cur[q] = row ? pg_ld_peer(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int c = 0; c < n_chunks; ++c) {
-            const int s = c % PG_STAGES;
-            if (c + 1 < T) {
-                const float* row = row_of(c + 1);
+        for (int j = 0; j < PG_DEPTH; ++j) issue(j, buf[j]);
+        for (int c0 = 0; c0 < n_chunks; c0 += PG_DEPTH) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) nxt[q] = row ? pg_ld_peer(row + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            uint4 packs[8];
-            if (c < T) {
+            for (int j = 0; j < PG_DEPTH; ++j) {
+                const int c = c0 + j;
+                if (c < n_chunks) {
+                    const int s = c % PG_STAGES;
+                    uint4 pk[2];
+                    if (c < T) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    packs[q].x = tfy_pack_bf16x2(cur[2 * q].x, cur[2 * q].y);
-                    packs[q].y = tfy_pack_bf16x2(cur[2 * q].z, cur[2 * q].w);
-                    packs[q].z = tfy_pack_bf16x2(cur[2 * q + 1].x, cur[2 * q + 1].y);
-                    packs[q].w = tfy_pack_bf16x2(cur[2 * q + 1].z, cur[2 * q + 1].w);
+                        for (int h = 0; h < 2; ++h) {
+                            pk[h].x = tfy_pack_bf16x2(buf[j][2 * h].x, buf[j][2 * h].y);
+                            pk[h].y = tfy_pack_bf16x2(buf[j][2 * h].z, buf[j][2 * h].w);
+                            pk[h].z = tfy_pack_bf16x2(buf[j][2 * h + 1].x, buf[j][2 * h + 1].y);
+                            pk[h].w = tfy_pack_bf16x2(buf[j][2 * h + 1].z, buf[j][2 * h + 1].w);
+                        }
+                    } else {
+                        float f[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q)
+                            f[q] = (live && p * 16 + q < n_num) ? numeric[(size_t)b * n_num + p * 16 + q] : 0.f;
+                        pk[0] = TfyPack<__nv_bfloat16>::pack(f);
+                        pk[1] = TfyPack<__nv_bfloat16>::pack(f + 8);
+                    }
+                    if (c >= PG_STAGES) pg_mbar_wait(&empty[s], ((c / PG_STAGES) - 1) & 1);
+                    uint8_t* a_row = ring + (size_t)s * PG_STAGE_BYTES + r * 128;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        *reinterpret_cast<uint4*>(a_row + (((2 * p + h) ^ (r & 7)) << 4)) = pk[h];
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    pg_mbar_arrive(&full_a[s]);
+                    if (live) {                          // keep the activations for the backward (dW = dy^T x)
+                        __nv_bfloat16* xr = xbuf + (size_t)b * Kp + c * 64 + p * 16;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            if (c * 64 + p * 16 + h * 8 + 8 <= Kp) tfy_st16(xr + h * 8, pk[h]);
+                    }
+                    issue(c + PG_DEPTH, buf[j]);         // refill this slot (zeros beyond the last table)
                 }
-            } else {
-                float f[64];
-#pragma unroll
-                for (int q = 0; q < 64; ++q) f[q] = (live && q < n_num) ? numeric[(size_t)b * n_num + q] : 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) packs[q] = TfyPack<__nv_bfloat16>::pack(f + q * 8);
             }
-            if (c >= PG_STAGES) pg_mbar_wait(&empty[s], ((c / PG_STAGES) - 1) & 1);
-            uint8_t* a_row = ring + (size_t)s * PG_STAGE_BYTES + r * 128;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(a_row + ((q ^ (r & 7)) << 4)) = packs[q];
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            pg_mbar_arrive(&full_a[s]);
-            if (live) {                                  // keep the activations for the backward (dW = dy^T x)
-                __nv_bfloat16* xr = xbuf + (size_t)b * Kp + c * 64;
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (c * 64 + q * 8 + 8 <= Kp) tfy_st16(xr + q * 8, packs[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) cur[q] = nxt[q];
         }
+        if (warp >= 6) goto pg_done;                     // warps 2-5 go on to the epilogue
         // ===== epilogue: bias, bf16, row-contiguous 16-byte stores =====
         const int quad = warp & 3;
         const int row = quad * 32 + lane;                 // TMEM lane == accumulator row of this thread
@@ -253,6 +259,7 @@ tfy_ps_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const uint6
             }
         }
     }
+pg_done:
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
