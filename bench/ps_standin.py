@@ -28,6 +28,32 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+
+_STAGE = False   # gloo (more ranks than GPUs: the N=1 topology) cannot send CUDA tensors here: stage through the host
+
+
+def _send(t, dst):
+    dist.send(t.detach().cpu() if _STAGE else t, dst=dst)
+
+
+def _recv(t, src):
+    if _STAGE:
+        h = torch.empty(t.shape, dtype=t.dtype)
+        dist.recv(h, src=src)
+        t.copy_(h)
+    else:
+        dist.recv(t, src=src)
+
+
+def _bcast(t, src):
+    if _STAGE:
+        h = t.detach().cpu()
+        dist.broadcast(h, src=src)
+        t.copy_(h)
+    else:
+        dist.broadcast(t, src=src)
+
+
 def run(args) -> int:
     from bench import wide_deep
     n_chief, n_worker, n_ps = wide_deep.topology(args.gpus)
@@ -63,7 +89,9 @@ def main():
     ngpu = torch.cuda.device_count()
     torch.cuda.set_device(local % ngpu)
     common.quiet_nccl()
-    dist.init_process_group("nccl" if world <= ngpu else "gloo")
+    global _STAGE
+    _STAGE = world > ngpu
+    dist.init_process_group("gloo" if _STAGE else "nccl")
     dev = torch.device("cuda")
     T, P = a.trainers, a.ps
     B, V, E, NC, NN = wd.BATCH, wd.VOCAB, wd.EMB, wd.N_CAT, wd.N_NUM
@@ -101,23 +129,23 @@ def main():
         while True:                                          # serve rounds until rank 0 says stop
             for w in range(T):
                 ids = torch.empty((NC, B), dtype=torch.int64, device=dev)
-                dist.recv(ids, src=w)
+                _recv(ids, src=w)
                 rows_d = torch.stack([deep_t[t][ids[t]] for t in deep_t]) if nd else torch.empty(0, device=dev)
                 rows_w = torch.stack([wide_t[t][ids[t]] for t in wide_t]) if nw else torch.empty(0, device=dev)
                 if nd:
-                    dist.send(rows_d, dst=w)
+                    _send(rows_d, dst=w)
                 if nw:
-                    dist.send(rows_w, dst=w)
-                dist.send(dense, dst=w)
+                    _send(rows_w, dst=w)
+                _send(dense, dst=w)
                 if nd:
                     gd = torch.empty_like(rows_d)
-                    dist.recv(gd, src=w)
+                    _recv(gd, src=w)
                     for k, t in enumerate(deep_t):                 # sparse Adagrad on the touched rows
                         deep_acc[t].index_add_(0, ids[t], gd[k] * gd[k])
                         deep_t[t].index_add_(0, ids[t], -lr * gd[k] / (deep_acc[t][ids[t]].sqrt() + 1e-7))
                 if nw:
                     gw = torch.empty_like(rows_w)
-                    dist.recv(gw, src=w)
+                    _recv(gw, src=w)
                     for k, t in enumerate(wide_t):                 # sparse FTRL on the touched rows
                         i_ = ids[t]
                         n_old = wide_n[t][i_]
@@ -127,11 +155,11 @@ def main():
                         wide_z[t][i_] = z
                         wide_t[t][i_] = -z / (n_new.sqrt() / lr)
                 gdense = torch.empty_like(dense)
-                dist.recv(gdense, src=w)
+                _recv(gdense, src=w)
                 dense_acc.addcmul_(gdense, gdense)
                 dense.addcdiv_(gdense, dense_acc.sqrt().add_(1e-7), value=-lr)
             flag = torch.zeros(1, device=dev)
-            dist.broadcast(flag, src=0)
+            _bcast(flag, src=0)
             if flag.item() > 0:
                 break
         dist.barrier()
@@ -153,18 +181,18 @@ def main():
         ids = (raw * 2654435761 % (2 ** 32)) % V
         rows_d, rows_w, dense_parts = {}, {}, {}
         for p in range(P):
-            dist.send(ids, dst=T + p)
+            _send(ids, dst=T + p)
             nd, nw = len(owned(deep_owner, p)), len(owned(wide_owner, p))
             if nd:
                 rd = torch.empty((nd, B, E), device=dev)
-                dist.recv(rd, src=T + p)
+                _recv(rd, src=T + p)
                 rows_d[p] = rd.requires_grad_(True)
             if nw:
                 rw = torch.empty((nw, B, 1), device=dev)
-                dist.recv(rw, src=T + p)
+                _recv(rw, src=T + p)
                 rows_w[p] = rw.requires_grad_(True)
             dn = torch.empty(sum(dense_sizes[i] for i in owned(dense_owner, p)), device=dev)
-            dist.recv(dn, src=T + p)
+            _recv(dn, src=T + p)
             dense_parts[p] = dn.requires_grad_(True)
         var = {}
         for p in range(P):
@@ -191,12 +219,12 @@ def main():
         loss.backward()
         for p in range(P):
             if p in rows_d:
-                dist.send(rows_d[p].grad, dst=T + p)
+                _send(rows_d[p].grad, dst=T + p)
             if p in rows_w:
-                dist.send(rows_w[p].grad, dst=T + p)
-            dist.send(dense_parts[p].grad, dst=T + p)
+                _send(rows_w[p].grad, dst=T + p)
+            _send(dense_parts[p].grad, dst=T + p)
         flag = torch.zeros(1, device=dev)
-        dist.broadcast(flag, src=0)                      # rank 0 tells the ps ranks when to stop serving
+        _bcast(flag, src=0)                      # rank 0 tells the ps ranks when to stop serving
         return loss.item() if sync_loss else loss
 
     for _ in range(warm):
@@ -221,20 +249,20 @@ def main():
     raw = torch.stack([feats[f"c{t}"][:, 0] for t in range(NC)]).to(dev)
     ids = (raw * 2654435761 % (2 ** 32)) % V
     for p in range(P):
-        dist.send(ids, dst=T + p)
+        _send(ids, dst=T + p)
         nd, nw = len(owned(deep_owner, p)), len(owned(wide_owner, p))
         if nd:
-            rd = torch.empty((nd, B, E), device=dev); dist.recv(rd, src=T + p)
+            rd = torch.empty((nd, B, E), device=dev); _recv(rd, src=T + p)
         if nw:
-            rw = torch.empty((nw, B, 1), device=dev); dist.recv(rw, src=T + p)
-        dn = torch.empty(sum(dense_sizes[i] for i in owned(dense_owner, p)), device=dev); dist.recv(dn, src=T + p)
+            rw = torch.empty((nw, B, 1), device=dev); _recv(rw, src=T + p)
+        dn = torch.empty(sum(dense_sizes[i] for i in owned(dense_owner, p)), device=dev); _recv(dn, src=T + p)
         if nd:
-            dist.send(torch.zeros_like(rd), dst=T + p)
+            _send(torch.zeros_like(rd), dst=T + p)
         if nw:
-            dist.send(torch.zeros_like(rw), dst=T + p)
-        dist.send(torch.zeros_like(dn), dst=T + p)
+            _send(torch.zeros_like(rw), dst=T + p)
+        _send(torch.zeros_like(dn), dst=T + p)
     flag = torch.ones(1, device=dev)
-    dist.broadcast(flag, src=0)
+    _bcast(flag, src=0)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

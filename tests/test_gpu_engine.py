@@ -389,6 +389,32 @@ def test_overlapped_exchange_matches_single_launch(monkeypatch):
     assert rel < 0.02, rel
 
 
+def test_fused_splitk_epilogue_matches_two_launch_path(monkeypatch):
+    """TFY_SPLITK_FUSE=1 (bias / ReLU / dropout applied by the split-K GEMM's own CTAs after they meet on the tile
+    counter) trains like the default GEMM + bias_act_drop pair: same dropout stream, same loss trajectory."""
+    import numpy as np
+    from tf_yarn_b200 import keras
+
+    def run(fuse):
+        monkeypatch.setenv("TFY_SPLITK_FUSE", "1" if fuse else "0")
+        torch.manual_seed(7)
+        m = _mnist_like(0.25, 0.5)
+        m.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True),
+                  optimizer=keras.optimizers.Adadelta(1.0))
+        rs = np.random.RandomState(0)
+        y = rs.randint(0, 10, 512).astype("int64")
+        x = (rs.rand(512, 28, 28, 1) * 0.5 + (y[:, None, None, None] / 20.0)).astype("float32")
+        h = m.fit(torch.from_numpy(x), torch.from_numpy(y), batch_size=128, epochs=3, shuffle=False, verbose=0)
+        torch.cuda.synchronize()
+        return m._engine, m._engine.fused.master.clone(), h.history["loss"]
+
+    e0, m0, l0 = run(False)
+    e1, m1, l1 = run(True)
+    assert e1._launches_per_step == e0._launches_per_step - 1
+    assert all(abs(a - b) <= 0.03 * max(abs(a), 1e-3) + 0.01 for a, b in zip(l0, l1)), (l0, l1)
+    assert ((m1 - m0).norm() / m0.norm()).item() < 0.02
+
+
 @pytest.mark.parametrize("shape", [(256, 256, 64), (512, 768, 512), (1000, 520, 264), (4096, 1024, 128), (130, 304, 72)])
 def test_tcgen05_2cta_gemm_matches_fp32_reference(shape):
     """Persistent cta_group::2 GEMM (256x256 tiles of a CTA pair, double-buffered TMEM, TMA-store epilogue) vs fp32."""

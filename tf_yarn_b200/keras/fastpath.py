@@ -15,7 +15,7 @@ the step does not go through autograd at all:
 * weight gradients are written straight into the flat gradient buffer consumed by the fused
   reduce-scatter / optimizer / all-gather kernel (no ``grad += g`` accumulation launches).
 
-9 launches per MNIST-CNN step, all of them our kernels (no cuBLAS / cuDNN), against 53 for the autograd engine
+10 launches per MNIST-CNN step, all of them our kernels (no cuBLAS / cuDNN), against 53 for the autograd engine
 (profiles/launches_*.csv).  Layers or shapes outside the kernels' envelope fall back to cuDNN / cuBLAS +
 the element-wise fused kernels of ``tfy_nn.cu``; models outside the grammar use the autograd engine
 (:class:`GraphTrainEngine`).
@@ -385,13 +385,18 @@ class FastSequentialEngine(GraphTrainEngine):
                     # tcgen05 kernel; partial sums meet in an fp32 accumulator that the epilogue clears
                     acc = self._splitk_acc(li, B, ly.units)
                     z = torch.empty((B, ly.units), dtype=bf16, device=cur.device)
-                    if os.environ.get("TFY_NO_SPLITK_FUSE") != "1":
-                        # ONE launch: the CTA that completes a tile applies bias + ReLU + dropout, writes the bf16
-                        # activations and the gate mask and clears the accumulator (last-arriver epilogue)
+                    tiles = ((B + 127) // 128) * ((ly.units + 127) // 128)
+                    co_resident = tiles * split <= torch.cuda.get_device_properties(cur.device).multi_processor_count
+                    if co_resident and os.environ.get("TFY_SPLITK_FUSE") == "1":
+                        # ONE launch (opt-in): the K-slice CTAs of a tile meet on a counter, then each applies bias +
+                        # ReLU + dropout to 1/split of the tile, writes the bf16 activations and the gate mask and
+                        # clears the accumulator.  (The slices spin on each other: the grid must be co-resident.)
+                        # Measured on B200 (profiles/r2/README.md): 84.9 us/step against 83.0 us for the two-launch
+                        # path below -- the fence + counter + spin costs more than the PDL-overlapped second launch
+                        # it removes, so two launches stay the default.
                         key = ("splitk_cnt", li)
                         if key not in self._acc32:
-                            tiles = ((B + 127) // 128) * ((ly.units + 127) // 128)
-                            self._acc32[key] = torch.zeros(tiles, dtype=torch.int32, device=cur.device)
+                            self._acc32[key] = torch.zeros(2 * tiles, dtype=torch.int32, device=cur.device)
                         self._chk(lib.tfy_gemm_bf16_splitk_fused(
                             xin.data_ptr(), w.data_ptr(), acc.data_ptr(), self._acc32[key].data_ptr(), b.data_ptr(),
                             z.data_ptr(), mask.data_ptr() if mask is not None else None, B, ly.units, K,

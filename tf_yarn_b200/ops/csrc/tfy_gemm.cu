@@ -112,7 +112,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 // applies bias + ReLU + dropout and writes the bf16 activations and the gradient-gate mask -- the work of the
 // separate tfy_bias_act_drop_fwd_f32 launch of round 1 (same element indexing, same random numbers).
 struct TfySplitKEpilogue {
-    uint32_t* counters;      // one per output tile, zero on entry, left zero
+    uint32_t* counters;      // two per output tile (arrive, finish), zero on entry, left zero
     __nv_bfloat16* y;        // [M, N] bf16 activations (row pitch ldy)
     uint8_t* mask;           // [M, N] bytes: 1 = gradient flows (optional)
     const TfyOptHyper* hp;   // dropout step counter
@@ -253,25 +253,30 @@ tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
     }
     if (out_mode == 2 && warp >= 2) {
-        // ---- fused split-K epilogue: the four epilogue warps of the CTA that completes the tile ----
-        __shared__ uint32_t s_last;
+        // ---- fused split-K epilogue, spread over ALL K-slice CTAs of the tile ----
+        // Every CTA arrives on the tile's counter after its red.adds, waits until all gridDim.z slices have arrived
+        // (they are co-resident: the host only selects this mode when the whole grid fits the SMs) and then finishes
+        // 1/gridDim.z of the tile: one 8-element group per thread, i.e. ONE L2 round trip.  (A first version let the
+        // last-arriving CTA finish the whole 128x128 tile alone: 16 dependent L2 round trips per thread, +9 us.)
+        uint32_t* cnt = ep.counters + 2 * (blockIdx.y * gridDim.x + blockIdx.x);
         asm volatile("bar.sync 1, 128;" ::: "memory");                 // this CTA's red.adds are all issued
         if (threadIdx.x == 64) {
             __threadfence();
-            uint32_t* cnt = ep.counters + blockIdx.y * gridDim.x + blockIdx.x;
-            const uint32_t prev = atomicAdd(cnt, 1u);
-            s_last = (prev == gridDim.z - 1) ? 1u : 0u;
-            if (s_last) *cnt = 0u;                                     // re-armed for the next launch / graph replay
+            atomicAdd(cnt, 1u);
+            while (*reinterpret_cast<volatile uint32_t*>(cnt) < gridDim.z) {
+            }
+            __threadfence();
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (s_last) {
-            __threadfence();
+        {
             const uint32_t step = ep.hp ? (uint32_t)ep.hp->step : 0u;
             const float keep_scale = ep.drop_rate > 0.f ? 1.f / (1.f - ep.drop_rate) : 1.f;
             const int t = threadIdx.x - 64;                            // 0..127
             const int G = N / 8;                                       // 8-element groups per row (N % 8 == 0)
-            const int tile_g = BN / 8;
-            for (int i = t; i < BM * tile_g; i += 128) {
+            constexpr int tile_g = BN / 8, tile_groups = BM * tile_g;
+            const int per = (tile_groups + (int)gridDim.z - 1) / (int)gridDim.z;
+            const int lo = (int)blockIdx.z * per, hi = min(lo + per, tile_groups);
+            for (int i = lo + t; i < hi; i += 128) {
                 const int r = i / tile_g, gq = i % tile_g;
                 const int row = m0 + r, n = n0 + gq * 8;
                 if (row >= M || n >= N) continue;
@@ -302,6 +307,14 @@ tfy_gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 }
                 tfy_st16(ep.y + (size_t)row * ep.ldy + n, TfyPack<__nv_bfloat16>::pack(v));
                 if (ep.mask) *reinterpret_cast<uint2*>(ep.mask + (size_t)row * N + n) = make_uint2(m_lo, m_hi);
+            }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {                                       // the CTA that finishes last re-arms both counters
+            __threadfence();
+            if (atomicAdd(cnt + 1, 1u) == gridDim.z - 1) {
+                cnt[0] = 0u;
+                cnt[1] = 0u;
             }
         }
     }
@@ -381,8 +394,9 @@ int tfy_gemm_bf16(const void* A, const void* B, void* C, float* C32, const void*
 }
 
 // Split-K GEMM with the fused epilogue: y[M,N] (bf16) = dropout(act(A . B^T + bias)), mask[M,N] (optional bytes).
-// acc32 [M,N] fp32 (row pitch N) is scratch that must be zero on entry and is left zero; counters: one uint32 per
-// 128x128 output tile, zero on entry, left zero.  N % 8 == 0.
+// acc32 [M,N] fp32 (row pitch N) is scratch that must be zero on entry and is left zero; counters: two uint32 per
+// 128x128 output tile, zero on entry, left zero.  N % 8 == 0.  The K-slice CTAs of a tile meet on a counter, so the
+// whole grid must be co-resident: returns -8 when tiles x split_k exceeds the SM count (use the two-launch path).
 int tfy_gemm_bf16_splitk_fused(const void* A, const void* B, float* acc32, uint32_t* counters, const void* bias, void* y,
                                void* mask, int M, int N, int K, int lda, int ldb, int relu, float drop_rate, uint32_t seed,
                                const TfyOptHyper* hp, int split_k, cudaStream_t s) {
@@ -406,6 +420,15 @@ int tfy_gemm_bf16_splitk_fused(const void* A, const void* B, float* acc32, uint3
     ep.counters = counters; ep.y = (__nv_bfloat16*)y; ep.mask = (uint8_t*)mask; ep.hp = hp;
     ep.drop_rate = drop_rate; ep.seed = seed; ep.ldy = N;
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, split_k);
+    {
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        if ((int)(grid.x * grid.y * grid.z) > sms) return -8;
+    }
     tfy_launch_pdl((tfy_gemm_bf16_kernel), dim3(grid), dim3(GEMM_THREADS), SMEM_BYTES, s, ma, mb, (__nv_bfloat16*)nullptr,
                    acc32, (const __nv_bfloat16*)bias, M, N, K, N, relu, 2, per, ep);
     return (int)cudaGetLastError();
