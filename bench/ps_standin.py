@@ -65,7 +65,8 @@ def run(args) -> int:
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     if res.returncode != 0 or not lines:
-        sys.stderr.write(res.stderr[-3000:])
+        tb = [ln for ln in res.stderr.splitlines() if "]:" in ln or "Error" in ln]
+        sys.stderr.write("\n".join(tb[:60]) + "\n" + res.stderr[-3000:])
         print(json.dumps({"impl": "standin", "config": "wide_deep", "error": f"rc={res.returncode}"}))
         return 1
     print(lines[-1], flush=True)
