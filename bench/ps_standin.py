@@ -33,10 +33,13 @@ _STAGE = False   # gloo (more ranks than GPUs: the N=1 topology) cannot send CUD
 
 
 def _send(t, dst):
+    import torch.distributed as dist
     dist.send(t.detach().cpu() if _STAGE else t, dst=dst)
 
 
 def _recv(t, src):
+    import torch
+    import torch.distributed as dist
     if _STAGE:
         h = torch.empty(t.shape, dtype=t.dtype)
         dist.recv(h, src=src)
@@ -46,6 +49,7 @@ def _recv(t, src):
 
 
 def _bcast(t, src):
+    import torch.distributed as dist
     if _STAGE:
         h = t.detach().cpu()
         dist.broadcast(h, src=src)

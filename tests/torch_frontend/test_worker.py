@@ -1,7 +1,6 @@
 import os
 from unittest import mock
 
-import pytest
 import torch
 
 from tf_yarn_b200.pytorch import DataLoaderArgs

@@ -8,7 +8,7 @@ estimator is the BASELINE config that exercises the parameter-server path.
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Dict, List, Optional, Sequence
+from typing import Any, Callable, Dict, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -17,7 +17,7 @@ import torch.nn.functional as F
 from tf_yarn_b200.estimator import feature_column as fc
 from tf_yarn_b200.estimator.config import RunConfig
 from tf_yarn_b200.estimator.estimator import Estimator
-from tf_yarn_b200.estimator.spec import EstimatorSpec, ModeKeys
+from tf_yarn_b200.estimator.spec import EstimatorSpec
 
 
 def _classification_loss(n_classes: int) -> Callable:

@@ -23,7 +23,6 @@ import os
 import shutil
 import signal
 import subprocess
-import sys
 import tempfile
 import time
 import uuid

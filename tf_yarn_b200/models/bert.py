@@ -4,7 +4,6 @@ Horovod-path" configuration.  Not in the reference tree; it exercises the all-re
 """
 from __future__ import annotations
 
-import math
 from typing import Dict
 
 import torch

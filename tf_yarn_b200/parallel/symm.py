@@ -17,7 +17,6 @@ from __future__ import annotations
 import ctypes
 import os
 import tempfile
-import time
 import uuid
 from typing import Optional, Sequence
 

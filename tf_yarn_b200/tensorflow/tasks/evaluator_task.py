@@ -17,7 +17,7 @@ import os
 import re
 import time
 from datetime import datetime, timedelta
-from typing import Callable, Optional, Set
+from typing import Callable, Set
 
 from tf_yarn_b200 import _task_commons, event
 from tf_yarn_b200._task_commons import TaskClient, get_task, get_task_key, setup_logging

@@ -4,7 +4,7 @@ from __future__ import annotations
 import logging
 import re
 import sys
-from typing import Dict, List, Optional, Tuple, Union
+from typing import List, Optional, Tuple, Union
 
 from tf_yarn_b200 import event
 from tf_yarn_b200._internal import MonitoredThread
