@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # Race / memory checking of the single-GPU kernels (run on a B200 through gpurun):
-#   gpurun --timeout 1500 -- tools/sanitize.sh
+#   gpurun --timeout 1500 -- tools/sanitize.sh          (SAN_TIMEOUT=<s> bounds each run; rc=124 = cut off, not an error)
 # Writes gpurun_out/sanitizer_<tool>_<suite>.log plus a one-line-per-run summary (sanitizer_summary.txt) and
 # FAILS (exit 1) when a tool reports an error.  The reference has no sanitizer usage at all.
 # Cross-GPU flag protocols (system-scope release/acquire over NVLink) are outside what racecheck models; the
@@ -14,12 +14,12 @@ status=0
 run() {  # tool suite command...
   local tool=$1 suite=$2; shift 2
   local log="$OUT/sanitizer_${tool}_${suite}.log"
-  timeout 1200 compute-sanitizer --tool "$tool" --error-exitcode 99 --log-file "$log" "$@" > "$OUT/sanitizer_${tool}_${suite}.out" 2>&1
+  timeout ${SAN_TIMEOUT:-1200} compute-sanitizer --tool "$tool" --error-exitcode 99 --log-file "$log" "$@" > "$OUT/sanitizer_${tool}_${suite}.out" 2>&1
   local rc=$?
   local verdict
   verdict=$(grep -E "ERROR SUMMARY|RACECHECK SUMMARY" "$log" | tail -1)
   echo "$tool $suite rc=$rc :: ${verdict:-no summary line}" | tee -a "$SUMMARY"
-  if [ $rc -ne 0 ]; then status=1; fi
+  if [ $rc -ne 0 ] && [ $rc -ne 124 ]; then status=1; fi
 }
 K="nn_kernels or fused_step_local or tcgen05 or dense_head or dense_backward"
 run memcheck  engine python -m pytest tests/test_gpu_engine.py -m gpu -q -x -k "$K"
