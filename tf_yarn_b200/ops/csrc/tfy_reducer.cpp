@@ -64,6 +64,7 @@ struct Reducer {
         cudaEventRecord(k.ready, cur);
         cudaStreamWaitEvent(comm, k.ready, 0);
         int rc;
+        bool launched = true;
         if (k.fused) {
             // zero_grads = 1: the kernel clears the bucket behind itself (autograd accumulates into it next step)
             rc = tfy_fused_step_shard_range(&ctx, k.dtype, k.param_dtype, k.opt, k.mode, k.grad_off, k.param_off,
@@ -71,10 +72,11 @@ struct Reducer {
         } else if (ctx.world > 1) {
             rc = tfy_allreduce(&ctx, k.dtype, algo, k.grad_off, k.n, 1.0f / (float)ctx.world, nullptr, 0, 0, comm);
         } else {
-            rc = 0;
+            rc = 0;                  // one rank, no optimizer fused: nothing to exchange
+            launched = false;
         }
         cudaEventRecord(k.done, comm);
-        if (rc == 0) ++launches;
+        if (rc == 0 && launched) ++launches;
         else last_error = rc;
         last_launched = b;
         return rc;
@@ -94,6 +96,8 @@ struct Reducer {
 
 extern "C" {
 
+void tfy_reducer_destroy(void* h);
+
 // offs / ns / dtypes / n_params: one entry per bucket; param_bucket: bucket index of every parameter.
 void* tfy_reducer_create(const TfyCommCtx* ctx, int n_buckets, const uint64_t* offs, const size_t* ns, const int* dtypes,
                          const int* n_params, int n_total_params, const int* param_bucket, int algo) {
@@ -110,7 +114,7 @@ void* tfy_reducer_create(const TfyCommCtx* ctx, int n_buckets, const uint64_t* o
         k.pending = n_params[b];
         if (cudaEventCreateWithFlags(&k.ready, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&k.done, cudaEventDisableTiming) != cudaSuccess) {
-            delete r;
+            tfy_reducer_destroy(r);      // also releases the events created so far
             return nullptr;
         }
     }
@@ -118,7 +122,8 @@ void* tfy_reducer_create(const TfyCommCtx* ctx, int n_buckets, const uint64_t* o
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&r->comm, cudaStreamNonBlocking, hi) != cudaSuccess) {
-        delete r;
+        r->comm = nullptr;
+        tfy_reducer_destroy(r);
         return nullptr;
     }
     return r;
@@ -141,6 +146,7 @@ int tfy_reducer_set_fused(void* h, int bucket, int param_dtype, uint64_t param_o
 // called from the post-accumulate-grad hook of parameter `param`; `cur` = the stream backward runs on
 int tfy_reducer_mark_ready(void* h, int param, cudaStream_t cur) {
     auto* r = (Reducer*)h;
+    if (!r || param < 0 || param >= (int)r->param_bucket.size()) return -2;
     Bucket& k = r->buckets[r->param_bucket[param]];
     if (k.pending > 0 && --k.pending == 0) return r->launch_ready_prefix(cur);
     return 0;

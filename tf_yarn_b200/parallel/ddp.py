@@ -367,7 +367,8 @@ def wrap_model(model: nn.Module, device, ddp_kwargs: Optional[dict] = None, comm
     """Data-parallel wrapper appropriate for the process: ours on B200, torch DDP on CPU/gloo."""
     import torch.distributed as dist
     ddp_kwargs = dict(ddp_kwargs or {})
-    if isinstance(device, str) and device.startswith("cuda") or isinstance(device, int):
+    on_gpu = isinstance(device, int) or torch.device(device).type == "cuda"
+    if on_gpu:
         if comm is None:
             from tf_yarn_b200.parallel import runtime
             comm = runtime.get_communicator()
