@@ -73,7 +73,8 @@ def _get_step(checkpoint: str) -> int:
         if not ext or not root or re.fullmatch(r"\.\d+", ext):
             break
         stem = root
-    m = re.search(r"(\d+)(?!.*\d)", stem)
+    # "weights.02-0.35.h5" ({epoch:02d}-{val_loss:.2f}): a metric formatted as a float is not the step
+    m = re.search(r"(\d+)(?!.*\d)", re.sub(r"\d+\.\d+", "", stem)) or re.search(r"(\d+)(?!.*\d)", stem)
     if m is None:
         raise ValueError(f"cannot parse a training step out of checkpoint name {checkpoint!r}: use a "
                          "ModelCheckpoint filepath with {epoch} or a step number in it")
