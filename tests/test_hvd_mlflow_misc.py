@@ -132,3 +132,12 @@ def test_check_hadoop_env_entry_point_runs_the_whole_check(tmp_path, monkeypatch
     assert check_hadoop_env.main([]) == 0
     log = (tmp_path / check_hadoop_env.RESULT_CHECK_FILE).read_text()
     assert "remote_check: True" in log and "setup: OK" in log
+
+
+def test_hvd_broadcast_variables_alias_single_rank():
+    import torch
+    from tf_yarn_b200 import hvd
+    hvd.init()
+    t = torch.arange(4.0)
+    hvd.broadcast_variables([t], root_rank=0)          # one rank: nothing to exchange
+    assert t.tolist() == [0.0, 1.0, 2.0, 3.0]

@@ -131,3 +131,13 @@ def test_fast_path_plan_grammar():
     m4.compile(loss="mse", optimizer="adadelta")
     m4.build()
     assert fastpath.build_plan(m4) is None
+
+
+def test_keras_estimator_namespace_matches_tf_keras(tmp_path):
+    """tf.keras.estimator.model_to_estimator(model, config=RunConfig(model_dir=...)) (reference: examples/keras_example.py:64-65)."""
+    from tf_yarn_b200 import estimator as est
+    from tf_yarn_b200 import keras as k
+    m = k.Sequential([k.layers.Dense(3, input_shape=(4,))])
+    m.compile(loss="sparse_categorical_crossentropy", optimizer="sgd", metrics=["accuracy"])
+    e = k.estimator.model_to_estimator(m, config=est.RunConfig(model_dir=str(tmp_path)))
+    assert isinstance(e, est.Estimator) and e.model_dir == str(tmp_path)

@@ -223,6 +223,12 @@ def broadcast_parameters(params, root_rank: int = 0) -> None:
             broadcast_(t, root_rank)
 
 
+def broadcast_variables(variables, root_rank: int = 0) -> None:
+    """``horovod.tensorflow.broadcast_variables``: same as :func:`broadcast_parameters` for a list of tensors /
+    parameters / ``(name, tensor)`` pairs or a ``state_dict``."""
+    broadcast_parameters(variables, root_rank)
+
+
 def broadcast_optimizer_state(optimizer: torch.optim.Optimizer, root_rank: int = 0) -> None:
     tensors = []
     for st in optimizer.state.values():

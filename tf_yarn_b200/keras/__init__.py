@@ -12,3 +12,10 @@ class models:  # namespace parity: keras.models.load_model / keras.models.Sequen
     load_model = staticmethod(load_model)
     Sequential = Sequential
     Model = Model
+
+
+class estimator:  # namespace parity: tf.keras.estimator.model_to_estimator (reference: examples/keras_example.py:64-65)
+    @staticmethod
+    def model_to_estimator(keras_model, model_dir=None, config=None, **kwargs):
+        from tf_yarn_b200.estimator.canned import model_to_estimator as _impl    # late: estimator imports keras
+        return _impl(keras_model, model_dir=model_dir, config=config, **kwargs)
