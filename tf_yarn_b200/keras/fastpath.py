@@ -339,6 +339,9 @@ class FastSequentialEngine(GraphTrainEngine):
                 else:
                     z = None
                 if z is None:
+                    self._warn_once(f"conv_fwd:{li}", f"Conv2D layer {li} ({Cin} -> {O} channels, {H}x{W}, batch {B}) is "
+                                    "outside the tcgen05 convolution kernels' envelope (C_in 32 / C_out 64 with ReLU + 2x2 "
+                                    "pool, or C_in 1): forward and backward use cuDNN")
                     xin = cur.to(bf16) if cur.dtype != bf16 else cur
                     zc = F.conv2d(xin.permute(0, 3, 1, 2), w)       # NCHW logical over NHWC bytes
                     z = zc.permute(0, 2, 3, 1)
@@ -411,6 +414,8 @@ class FastSequentialEngine(GraphTrainEngine):
                                                                 ly.units, int(st.relu), float(st.drop), seed, self._hp,
                                                                 s), "bias_act_drop_fwd_f32")
                 else:
+                    self._warn_once(f"dense_fwd:{li}", f"Dense layer {li} ({K} -> {ly.units}, batch {B}) is outside the "
+                                    "split-K tcgen05 GEMM's envelope (long K, at most 8 output tiles): forward uses cuBLAS")
                     z = torch.mm(xin, w.t())
                     self._chk(lib.tfy_bias_act_drop_fwd(z.data_ptr(), b.data_ptr(), z.data_ptr(),
                                                         mask.data_ptr() if mask is not None else None, B, ly.units,
@@ -446,6 +451,9 @@ class FastSequentialEngine(GraphTrainEngine):
                         self._acc32["head_counter"].data_ptr(), B, K, C, s), "dense_head_fused")
                     saved.append(("fused", dh))
                     continue
+                self._warn_once(f"head:{li}", f"classifier head {li} ({xin.shape[1]} -> {ly.units}, batch {B}) is outside "
+                                "the fused head kernel's envelope (K in 128/256/512, at most 16 classes, Dense "
+                                "predecessor): logits and gradients use cuBLAS")
                 logits = torch.mm(xin, w.t())
                 C = ly.units
                 dlogits = torch.empty((B, C), dtype=bf16, device=cur.device)
