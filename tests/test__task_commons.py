@@ -70,3 +70,29 @@ def test_roles(monkeypatch):
     assert _task_commons.is_chief("chief") and _task_commons.is_worker("worker")
     monkeypatch.setenv("TF_YARN_N_TRY", "2")
     assert _task_commons.n_try() == 2
+
+
+def test_sigterm_runs_atexit_hooks(tmp_path):
+    """The launcher stops tasks with SIGTERM: task programs turn it into a normal exit so atexit hooks run (the
+    parameter-server shards unlink their /dev/shm files there) and the status stays 143."""
+    import signal
+    import subprocess
+    import sys
+    import time
+    marker = tmp_path / "cleaned"
+    ready = tmp_path / "ready"
+    code = (
+        "import atexit, time, pathlib\n"
+        "from tf_yarn_b200 import _task_commons\n"
+        "_task_commons.setup_logging()\n"
+        f"atexit.register(lambda: pathlib.Path({str(marker)!r}).write_text('x'))\n"
+        f"pathlib.Path({str(ready)!r}).write_text('x')\n"
+        "time.sleep(60)\n")
+    p = subprocess.Popen([sys.executable, "-c", code])
+    deadline = time.time() + 60
+    while not ready.exists() and time.time() < deadline:
+        time.sleep(0.05)
+    assert ready.exists()
+    p.send_signal(signal.SIGTERM)
+    assert p.wait(30) == 128 + signal.SIGTERM
+    assert marker.exists()

@@ -156,11 +156,16 @@ def test_parameter_server_strategy_end_to_end(tmp_path):
     """chief + 2 workers + 2 ps + evaluator: async pull/push through the ps shards, stop barrier lets ps exit."""
     from tf_yarn_b200.estimator import summary
     from tf_yarn_b200.tensorflow import run_on_yarn
+    import glob
+    from tf_yarn_b200.estimator import ps as ps_cpu
+    shards_before = set(glob.glob(os.path.join(ps_cpu._shm_dir(), "tfy_ps_*")))
     model_dir = str(tmp_path / "model")
     metrics = run_on_yarn(_ps_experiment(model_dir),
                           {"chief": TaskSpec("1 GiB", 1), "worker": TaskSpec("1 GiB", 1, instances=2),
                            "ps": TaskSpec("1 GiB", 1, instances=2), "evaluator": TaskSpec("1 GiB", 1)})
     assert metrics.container_duration[ContainerKey("ps", 1)] is not None
+    # the ps tasks unlink their shared-memory shards on the way out (normal exit or the launcher's SIGTERM)
+    assert set(glob.glob(os.path.join(ps_cpu._shm_dir(), "tfy_ps_*"))) <= shards_before
     sc = summary.read_scalars(os.path.join(model_dir, "eval"))
     acc = [v for n, v in zip(sc["name"], sc["value"]) if n == "accuracy"]
     # the first evaluated checkpoint may already be a late one (asynchronous evaluator): require a trained model,

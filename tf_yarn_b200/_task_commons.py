@@ -27,6 +27,26 @@ _logger = logging.getLogger(__name__)
 def setup_logging() -> None:
     here = os.path.dirname(__file__)
     logging.config.fileConfig(os.path.join(here, "default.log.conf"), disable_existing_loggers=False)
+    exit_cleanly_on_sigterm()
+
+
+def exit_cleanly_on_sigterm() -> None:
+    """Turn the launcher's SIGTERM (application finished, failed or killed: launcher/local.py ``_kill_all``) into a
+    normal interpreter exit, so ``atexit`` hooks and ``finally`` blocks run: the parameter-server shards unlink
+    their /dev/shm files, KV connections close.  (YARN gives the reference's containers the same SIGTERM-then-
+    SIGKILL sequence.)  Only the main thread of the main interpreter can install it; the exit status stays 143."""
+    import signal
+    import threading
+    if threading.current_thread() is not threading.main_thread():
+        return
+
+    def _term(signum, frame):
+        raise SystemExit(128 + signum)
+
+    try:
+        signal.signal(signal.SIGTERM, _term)
+    except (ValueError, OSError):          # embedded interpreter / exotic platform: keep the default action
+        pass
 
 
 class TaskClient:

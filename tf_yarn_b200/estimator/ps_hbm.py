@@ -4,13 +4,16 @@ Every task of the training cluster (chief, workers AND ps) joins one symmetric a
 (:mod:`tf_yarn_b200.parallel.symm`, rendezvous through the launcher's KV store).  A ps rank's
 shard is a region of ITS arena; chief/workers reach it through the peer mapping over NVLink:
 
-* dense pull   : ``tfy_ps_pull``   -- peer fp32 master -> local replica, one launch for all variables;
-* GEMM pull    : ``tfy_gemm_bf16`` -- the weight matrix of a Dense layer is never copied: its bf16
-  shadow on the ps rank is streamed by TMA into the tcgen05 GEMM that consumes it (K5);
-* sparse pull  : ``tfy_ps_embedding_bag`` -- rows of the batch gathered from the peer table and
-  bag-reduced in the same kernel;
-* push         : ``tfy_ps_push`` / ``tfy_ps_push_rows`` -- gradients applied to the peer master with
-  vector red/atom (SGD, Adagrad), asynchronously and without locks (K6).
+* dense pull   : ``tfy_ps_pull`` -- peer fp32 master -> local replica, ONE launch for the variables that need a
+  local copy (biases, small vectors); Dense weights and embedding rows are never copied;
+* GEMM pull    : the weight matrix of a Dense layer stays on the ps rank: its row-padded bf16 shadow is streamed
+  by TMA into the tcgen05 GEMM that consumes it (forward ``tfy_gemm_bf16``, backward ``tfy_dense_bwd``: dW and
+  dx in one kernel against the same remote shadow);
+* sparse pull  : ``tfy_ps_embedding_bag`` / ``tfy_ps_multi_bag`` (all tables of a tower in one launch); for the
+  first deep layer the gather IS the A-operand producer of the GEMM (K5, ``tfy_ps_gather_gemm``);
+* push         : ``tfy_ps_push`` / ``tfy_ps_push_rows`` / ``tfy_ps_multi_push_rows`` -- gradients applied to the peer
+  master with vector red/atom and the variable's own optimizer fused (SGD, Adagrad, Adam, FTRL), asynchronously
+  and without locks (K6); row gradients are pushed straight out of column slices of the fused layer's dx.
 
 The ps process only owns memory and waits for the stop barrier: no server thread is on the data path.
 Control state (layout, readiness, global step) stays on the KV store / a shared-memory header, as in
