@@ -297,11 +297,40 @@ class Estimator:
 
         ctx = SessionRunContext(self, self._global_step)
         start_step = self._global_step
-        last_save_time, last_save_step = time.time(), self._global_step
-        last_log_time, last_log_step = time.time(), self._global_step
         item = first
         if self._network is not None:
             self._network.train()
+        # failure detection: a synchronous all-reduce step waits on the peer ranks inside a kernel; without a
+        # heartbeat a dead peer would hang this task instead of failing it (utils/watchdog.py)
+        from tf_yarn_b200.utils import watchdog
+        wd = watchdog.StepWatchdog(watchdog.default_timeout(distributed), "Estimator.train").start()
+        try:
+            item = self._train_loop(item, it, hooks, ctx, wd, distributed, steps, max_steps, start_step, writer,
+                                    writes_files, cfg)
+        finally:
+            wd.close()
+        loss = self._last_loss_t
+        self.last_loss = float(loss) if self._global_step > start_step else self.last_loss
+        if writes_files and (cfg.save_checkpoints_steps or cfg.save_checkpoints_secs) and \
+                self._global_step > start_step:
+            st = ckpt.get_checkpoint_state(self._model_dir)
+            if st is None or ckpt.step_of(st.model_checkpoint_path) != self._global_step:
+                self._save()
+        for h in hooks:
+            try:
+                h.end(None)
+            except TypeError:
+                h.end()
+        if writer is not None:
+            writer.flush()
+            writer.close()
+        logger.info("Loss for final step: %s.", self.last_loss)
+        return self
+
+    def _train_loop(self, item, it, hooks, ctx, wd, distributed, steps, max_steps, start_step, writer, writes_files,
+                    cfg):
+        last_save_time, last_save_step = time.time(), self._global_step
+        last_log_time, last_log_step = time.time(), self._global_step
         while item is not None:
             if max_steps is not None and self._global_step >= max_steps:
                 break
@@ -311,6 +340,7 @@ class Estimator:
             wants_step = [h for h in hooks if _wants_global_step(h.before_run(ctx))]
             prev_gs = self._global_step
             loss = self._train_step(features, labels, distributed)
+            wd.beat()
             self._last_loss_t = loss          # device scalar of this step (hooks may read it: one 4-byte D2H)
             if self._ps is not None:
                 self._global_step = self._ps.increment_global_step()
@@ -344,22 +374,7 @@ class Estimator:
             if ctx.stop_requested:
                 break
             item = next(it, None)
-        self.last_loss = float(loss) if self._global_step > start_step else self.last_loss
-        if writes_files and (cfg.save_checkpoints_steps or cfg.save_checkpoints_secs) and \
-                self._global_step > start_step:
-            st = ckpt.get_checkpoint_state(self._model_dir)
-            if st is None or ckpt.step_of(st.model_checkpoint_path) != self._global_step:
-                self._save()
-        for h in hooks:
-            try:
-                h.end(None)
-            except TypeError:
-                h.end()
-        if writer is not None:
-            writer.flush()
-            writer.close()
-        logger.info("Loss for final step: %s.", self.last_loss)
-        return self
+        return item
 
     def _ps_step_body(self, features, labels) -> torch.Tensor:
         """pull -> forward -> backward -> push against the parameter servers (kernels only: capturable)."""

@@ -66,6 +66,17 @@ def _as_tensor(a) -> torch.Tensor:
     return torch.as_tensor(np.asarray(a))
 
 
+class _NoWatchdog:
+    """Stand-in used when a loop runs outside ``fit`` (no watchdog armed)."""
+
+    @staticmethod
+    def beat() -> None:
+        pass
+
+
+_NO_WATCHDOG = _NoWatchdog()
+
+
 class _ArrayBatches:
     """Batches out of in-memory arrays; pinned host memory when feeding a GPU."""
 
@@ -138,6 +149,7 @@ class Model:
         self.use_cuda_graph = True
         self.use_fast_path = True
         self.history = None
+        self._watchdog = None             # utils.watchdog.StepWatchdog while fit() runs
         self._pending_broadcast_root: Optional[int] = None
         for layer in layers or []:
             self.add(layer)
@@ -277,6 +289,18 @@ class Model:
                                   {"epochs": epochs, "steps": steps_per_epoch, "verbose": verbose})
         self.history = history
         self.stop_training = False
+        from tf_yarn_b200.utils import watchdog
+        distributed = bool(getattr(self.optimizer, "distributed", False))
+        self._watchdog = watchdog.StepWatchdog(watchdog.default_timeout(distributed), "Model.fit").start()
+        try:
+            return self._fit_epochs(cbs, history, make_iter, infinite, initial_epoch, epochs, steps_per_epoch,
+                                    validation_data, validation_steps, batch_size, verbose)
+        finally:
+            self._watchdog.close()
+            self._watchdog = None
+
+    def _fit_epochs(self, cbs, history, make_iter, infinite, initial_epoch, epochs, steps_per_epoch, validation_data,
+                    validation_steps, batch_size, verbose):
         cbs.call("on_train_begin", None)
         it = make_iter() if infinite else None
         for epoch in range(initial_epoch, epochs):
@@ -314,6 +338,7 @@ class Model:
         loss_sum, n = 0.0, 0
         metric_sums: Dict[str, float] = {}
         step = 0
+        wd = self._watchdog or _NO_WATCHDOG
         while steps is None or step < steps:
             item = first if first is not None else next(it, None)
             first = None
@@ -323,6 +348,7 @@ class Model:
             if cbs.has_batch_hooks:
                 cbs.call("on_train_batch_begin", step, None)
             logs = eng.train_step(_as_struct(xb), _as_struct(yb))
+            wd.beat()
             loss_sum += float(logs["loss"])
             for k, v in logs.items():
                 if k != "loss":
@@ -343,6 +369,7 @@ class Model:
         loss_sum, n_read = 0.0, 0
         sync_every_step = cbs.needs_batch_logs
         hooks = cbs.has_batch_hooks
+        wd = self._watchdog or _NO_WATCHDOG
 
         def fetch():
             nonlocal first
@@ -370,6 +397,7 @@ class Model:
                 nxt = fetch() if more else None
                 if pending is not None:         # loss of the previous step: its graph finished long ago
                     pending[1].synchronize()
+                    wd.beat()                   # a step COMPLETED on the device (not merely queued)
                     loss_sum += float(eng.loss_host(pending[0]))
                     n_read += 1
                 pending = (slot, done)
@@ -421,6 +449,7 @@ class Model:
         m_den = [0.0] * len(fns)
         self.net.eval() if self.net is not None else None
         n = 0
+        wd = getattr(self, "_watchdog", None)
         with torch.no_grad():
             for item in it:
                 if steps is not None and n >= steps:
@@ -433,6 +462,8 @@ class Model:
                     m_num, m_den = [0.0] * len(fns), [0.0] * len(fns)
                 yb = _move(_as_struct(yb), self._device)
                 out = self.net(xb)
+                if wd is not None:
+                    wd.beat()
                 bs = out.shape[0]
                 if self._loss_fn is not None:
                     loss_sum += float(self._loss_fn(yb, out)) * bs

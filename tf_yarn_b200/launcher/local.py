@@ -228,7 +228,9 @@ class LocalApplication:
             failed = [p for p, c in zip(self.processes, codes) if c not in (None, 0)]
             if failed:
                 for p in failed:
-                    logger.error("task %s exited with code %s (log: %s)", p.key.to_kv_str(), p.returncode,
+                    why = " [step watchdog: no training progress, a peer rank is probably gone]" \
+                        if p.returncode == 75 else ""           # utils/watchdog.py EXIT_CODE
+                    logger.error("task %s exited with code %s%s (log: %s)", p.key.to_kv_str(), p.returncode, why,
                                  p.log_path)
                 self._finish(FinalStatus.FAILED)
             elif all(c == 0 for c in codes):
