@@ -395,8 +395,8 @@ class FastSequentialEngine(GraphTrainEngine):
                         # ReLU + dropout to 1/split of the tile, writes the bf16 activations and the gate mask and
                         # clears the accumulator.  (The slices spin on each other: the grid must be co-resident.)
                         # Measured on B200 (profiles/r2/README.md): 84.9 us/step against 83.0 us for the two-launch
-                        # path below -- the fence + counter + spin costs more than the PDL-overlapped second launch
-                        # it removes, so two launches stay the default.
+                        # path below -- the fence + counter + spin costs more than the 3 us second kernel of the same
+                        # CUDA graph it removes, so two launches stay the default.
                         key = ("splitk_cnt", li)
                         if key not in self._acc32:
                             self._acc32[key] = torch.zeros(2 * tiles, dtype=torch.int32, device=cur.device)
