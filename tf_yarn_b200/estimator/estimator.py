@@ -11,7 +11,9 @@ Three training data planes, chosen from the process's role:
 
 * local / single process  -- plain optimizer step;
 * all-reduce (``optimizer`` wrapped by ``hvd.DistributedOptimizer``) -- gradients
-  averaged across ranks (fused K4 kernel on B200, gloo on CPU);
+  averaged across ranks by ONE all-reduce kernel over the fusion buffer (NVLS / P2P kernels of
+  ``ops/csrc/tfy_comm.cu`` on B200, gloo on CPU), then the optimizer step (the fully fused
+  reduce-scatter -> optimizer -> all-gather kernel serves the Keras engines and the DDP wrapper);
 * parameter server (``TF_CONFIG`` lists ``ps`` tasks) -- parameters live on the ps
   ranks; workers pull before and push after every step, asynchronously
   (:mod:`tf_yarn_b200.estimator.ps`).
