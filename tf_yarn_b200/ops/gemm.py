@@ -1,4 +1,5 @@
-"""Python entry points of the tcgen05 GEMM (``ops/csrc/tfy_gemm.cu``)."""
+"""Python entry points of the tcgen05 GEMMs: one tile per CTA with split-K and a remote-B operand
+(``ops/csrc/tfy_gemm.cu``) and the persistent 2-CTA kernel for large problems (``ops/csrc/tfy_gemm2.cu``)."""
 from __future__ import annotations
 
 import ctypes
@@ -37,7 +38,10 @@ def gemm_bf16(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = N
     else:
         N, ldb, bp = int(b_rows), int(b_ld or K), int(b_ptr)
     s = torch.cuda.current_stream().cuda_stream
-    if (split_k <= 1 and impl != "1cta" and (impl == "2cta" or (M >= GEMM2_MIN_DIM and N >= GEMM2_MIN_DIM))
+    # the 2-CTA kernel stores its tiles with TMA: the output row pitch must be a multiple of 16 bytes ("auto" falls
+    # back to the one-tile-per-CTA kernel, whose epilogue handles any pitch; an explicit "2cta" fails loudly)
+    ldc_ok = (out.stride(0) if out is not None else N) % 8 == 0
+    if (split_k <= 1 and impl != "1cta" and (impl == "2cta" or (M >= GEMM2_MIN_DIM and N >= GEMM2_MIN_DIM and ldc_ok))
             and os.environ.get("TFY_GEMM2", "1") != "0"):
         if out is None:
             out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
