@@ -293,9 +293,10 @@ struct TfyPack<float> {
 // (all our grids are a single wave, so early dependents never take a slot a primary CTA still needs) and
 // then waits for the grids it depends on to complete and flush.  Under stream capture these become
 // programmatic edges of the CUDA graph: launch latency and each kernel's prologue (barrier init, TMEM
-// allocation, tensor-map prefetch) overlap the tail of the previous kernel.  Opt-in (TFY_PDL=1): measured on
-// the MNIST step it is a wash (fprop / first-layer wgrad -1 us each, dgrad +2.6 us with early dependents
-// resident; 103.3 vs 101.5 us per step, profiles/bench_ours_N1_pdl_r1m.json), so the default stays off.
+// allocation, tensor-map prefetch) overlap the tail of the previous kernel.  Opt-in (TFY_PDL=1).  On round 1's
+// kernel set it was a wash (103.3 vs 101.5 us per step, profiles/bench_ours_N1_pdl_r1m.json); on the final
+// round-2 step it measures 78.2 vs 84.0 us on one GPU (profiles/r2/README.md), but the GPU test-suite and the
+// multi-GPU runs have not been repeated with it yet, so the default is still off.
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ void tfy_pdl_sync() {
