@@ -3,7 +3,8 @@
 #   gpurun --timeout 1500 -- tools/sanitize.sh          (SAN_TIMEOUT=<s> bounds each run; rc=124 = cut off, not an error)
 # Writes gpurun_out/sanitizer_<tool>_<suite>.log plus a one-line-per-run summary (sanitizer_summary.txt) and
 # FAILS (exit 1) when a tool reports an error.  The reference has no sanitizer usage at all.
-# Cross-GPU flag protocols (system-scope release/acquire over NVLink) are outside what racecheck models; the
+# Cross-GPU flag protocols (system-scope release/acquire over NVLink) are outside what racecheck models: the
+# protocol is model-checked on the CPU (tests/test_barrier_protocol_model.py, every interleaving) and the
 # multi-GPU kernels are covered by tests/gpu/comm_check.py + ddp_check.py (pytest -m gpu on a multi-GPU box).
 set -uo pipefail
 OUT=${1:-gpurun_out}
