@@ -141,3 +141,26 @@ def test_hvd_broadcast_variables_alias_single_rank():
     t = torch.arange(4.0)
     hvd.broadcast_variables([t], root_rank=0)          # one rank: nothing to exchange
     assert t.tolist() == [0.0, 1.0, 2.0, 3.0]
+
+
+def test_packaging_zip_and_local_upload(tmp_path):
+    """Reference: tf_yarn/packaging.py (deprecated pass-throughs): the names still work on one box."""
+    import sys
+    import warnings
+    import zipfile
+    from tf_yarn_b200 import packaging
+    src = tmp_path / "proj"
+    (src / "pkg").mkdir(parents=True)
+    (src / "pkg" / "mod.py").write_text("X = 1\n")
+    z = packaging.zip_path(str(src), include_base_name=True, tmp_dir=str(tmp_path / "out1"))
+    assert sorted(zipfile.ZipFile(z).namelist()) == ["proj/pkg/mod.py"]
+    z2 = packaging.zip_path(str(src), include_base_name=False, tmp_dir=str(tmp_path / "out2"))
+    assert sorted(zipfile.ZipFile(z2).namelist()) == ["pkg/mod.py"]
+    dst = tmp_path / "shipped" / "proj.zip"
+    assert packaging.upload_zip(z, str(dst)) == str(dst) and dst.exists()
+    assert packaging.upload_zip(z) == z
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        exe, name = packaging.upload_env()
+    assert exe == sys.executable and w and issubclass(w[0].category, DeprecationWarning)
+    assert packaging.get_editable_requirements() == {} and packaging.get_default_fs() == "file://"

@@ -77,3 +77,17 @@ def test_results_table_reads_the_committed_bench_lines():
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches"):
         assert key in d, key
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["params_in_sync"] is True
+
+
+def test_component_map_paths_exist():
+    """docs/ComponentMap.md maps every SURVEY.md §2 row to files of this repo: none of them may be stale."""
+    import re
+    text = open(os.path.join(ROOT, "docs", "ComponentMap.md")).read()
+    paths = set(re.findall(r"`((?:tf_yarn_b200|tests|profiles|docs|tools|bench)/[A-Za-z0-9_./]+|setup\.py|setup\.cfg|"
+                           r"requirements\.txt|tests-requirements\.txt|README\.md|__graft_entry__\.py|"
+                           r"\.github/workflows/main\.yml)`", text))
+    assert len(paths) > 80
+    missing = [p for p in sorted(paths) if not os.path.exists(os.path.join(ROOT, p))]
+    assert missing == []
+    for row in range(1, 34):                                        # every §2.1 row is present
+        assert re.search(rf"^\| {row} \|", text, re.M), row

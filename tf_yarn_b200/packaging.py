@@ -17,6 +17,7 @@ def zip_path(py_dir: str, include_base_name: bool = True, tmp_dir: Optional[str]
     """Zip a directory (used by the reference to ship code); returns the archive path."""
     import tempfile
     tmp_dir = tmp_dir or tempfile.mkdtemp()
+    os.makedirs(tmp_dir, exist_ok=True)
     base = os.path.basename(os.path.normpath(py_dir))
     out = os.path.join(tmp_dir, base + ".zip")
     with zipfile.ZipFile(out, "w", zipfile.ZIP_DEFLATED) as zf:
