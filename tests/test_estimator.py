@@ -208,3 +208,35 @@ def test_ps_layout_carries_per_variable_optimizers():
     again = ps.Layout.from_json(lay.to_json())
     assert again.kinds == ["ftrl", "adagrad"] and again.var_slots == [2, 1]
     assert again.shard_elems[0] == 16 * 3 and again.shard_elems[1] == 16 * 2
+
+
+def test_latest_and_best_exporters_with_a_recording_estimator(tmp_path):
+    """LatestExporter keeps the N most recent numeric export directories; BestExporter exports only improvements."""
+
+    class FakeEstimator:
+        def __init__(self):
+            self.n = 0
+
+        def export_saved_model(self, export_path, checkpoint_path=None):
+            self.n += 1
+            out = os.path.join(export_path, str(1000 + self.n))
+            os.makedirs(out, exist_ok=True)
+            return out
+
+    fake = FakeEstimator()
+    latest = est.LatestExporter("latest", exports_to_keep=2)
+    path = str(tmp_path / "export" / "latest")
+    os.makedirs(path)
+    for i in range(4):
+        latest.export(fake, path, f"model.ckpt-{i}", {"loss": 1.0}, False)
+    assert sorted(os.listdir(path)) == ["1003", "1004"] and latest.name == "latest"
+
+    best = est.BestExporter("best")
+    bpath = str(tmp_path / "export" / "best")
+    os.makedirs(bpath)
+    outs = [best.export(fake, bpath, "c", {"loss": v}, False) for v in (0.9, 1.2, 0.5, 0.5)]
+    assert [o is not None for o in outs] == [True, False, True, False]
+
+    final = est.FinalExporter("final")
+    assert final.export(fake, bpath, "c", {"loss": 1.0}, False) is None
+    assert final.export(fake, bpath, "c", {"loss": 1.0}, True) is not None
