@@ -150,7 +150,7 @@ class EarlyStopping(Callback):
             self.best, self.wait = cur, 0
         else:
             self.wait += 1
-            if self.wait > self.patience:
+            if self.wait >= self.patience:         # Keras: stop after `patience` epochs without improvement
                 self.model.stop_training = True
 
 
