@@ -196,7 +196,16 @@ class MaxPooling2D(Layer):
 
 class AveragePooling2D(MaxPooling2D):
     def call(self, x, training):
-        return F.avg_pool2d(x, self.pool_size, self.strides)
+        if self.padding != "same":
+            return F.avg_pool2d(x, self.pool_size, self.strides)
+        # TF 'same': pad (possibly one more row / column at the end) and average over the REAL elements only
+        ph = max(0, (math.ceil(x.shape[2] / self.strides[0]) - 1) * self.strides[0] + self.pool_size[0] - x.shape[2])
+        pw = max(0, (math.ceil(x.shape[3] / self.strides[1]) - 1) * self.strides[1] + self.pool_size[1] - x.shape[3])
+        pads = (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2)
+        total = F.avg_pool2d(F.pad(x, pads), self.pool_size, self.strides)
+        ones = torch.ones((1, 1) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+        share = F.avg_pool2d(F.pad(ones, pads), self.pool_size, self.strides)
+        return total / share
 
 
 class GlobalAveragePooling2D(Layer):
@@ -282,6 +291,11 @@ class LayerNormalization(Layer):
 
     def build_module(self, input_shape):
         return nn.LayerNorm(input_shape[-1], eps=self.epsilon)
+
+    def call(self, x, training):
+        if x.dim() == 4:          # images are logical NCHW over NHWC bytes: normalise the channel axis, like Keras
+            return self.module(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        return self.module(x)
 
     def get_config(self):
         return {"name": self.name, "epsilon": self.epsilon}
