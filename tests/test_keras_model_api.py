@@ -1,0 +1,105 @@
+"""Model-level API of the mini-Keras facade on CPU: the calls the reference's examples and docs make
+(examples/keras_example.py:55-62, native_keras_with_gloo_example.py:65-90, README.md:104-113)."""
+import numpy as np
+import pytest
+import torch
+
+from tf_yarn_b200 import data, keras
+
+
+def _xy(n=96, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 4, generator=g)
+    return x, (x[:, 0] + x[:, 1] > 0).long()
+
+
+def _model():
+    m = keras.Sequential()
+    m.add(keras.layers.Dense(8, activation="relu", input_shape=(4,)))
+    m.add(keras.layers.Dense(2))
+    m.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True), optimizer=keras.optimizers.SGD(0.2),
+              metrics=["accuracy"])
+    m._device = torch.device("cpu")
+    return m
+
+
+def test_fit_with_validation_data_callables_and_history():
+    x, y = _xy()
+    xv, yv = _xy(32, seed=1)
+    m = _model()
+    h = m.fit(lambda: x, lambda: y, batch_size=16, epochs=6, verbose=1, validation_data=(xv, yv))
+    assert set(h.history) == {"loss", "accuracy", "val_loss", "val_accuracy"} and len(h.history["loss"]) == 6
+    assert h.history["loss"][-1] < h.history["loss"][0] and h.history["val_accuracy"][-1] > 0.7
+    loss, acc = m.evaluate(xv, yv, batch_size=8)
+    assert acc == pytest.approx(h.history["val_accuracy"][-1], abs=1e-6) and loss > 0
+    assert m.evaluate(xv, yv, return_dict=True).keys() == {"loss", "accuracy"}
+
+
+def test_fit_on_a_dataset_with_steps_per_epoch_and_stop_training():
+    x, y = _xy()
+    ds = data.Dataset.from_tensor_slices((x, y)).shuffle(96, seed=0).batch(16).repeat()
+    m = _model()
+    seen = []
+    cb = keras.callbacks.LambdaCallback(on_epoch_end=lambda e, logs: seen.append(e))
+    m.fit(ds, epochs=3, steps_per_epoch=4, verbose=0, callbacks=[cb])
+    assert seen == [0, 1, 2]
+
+    class StopAfterFirst(keras.callbacks.Callback):
+        def on_epoch_end(self, epoch, logs=None):
+            self.model.stop_training = True
+
+    h = _model().fit(x, y, batch_size=16, epochs=5, verbose=0, callbacks=[StopAfterFirst()])
+    assert len(h.history["loss"]) == 1
+    finite = data.Dataset.from_tensor_slices((x, y)).batch(32)          # cardinality known: no steps_per_epoch needed
+    h = _model().fit(finite, epochs=2, verbose=0)
+    assert len(h.history["loss"]) == 2
+
+
+def test_predict_call_weights_and_summary(tmp_path):
+    x, y = _xy(40)
+    m = _model()
+    m.fit(x, y, batch_size=8, epochs=1, verbose=0)
+    p = m.predict(x, batch_size=16)
+    assert isinstance(p, np.ndarray) and p.shape == (40, 2)
+    assert np.allclose(p, m(x).detach().numpy(), atol=1e-6)
+    assert np.allclose(m.predict(x, batch_size=16, steps=1), p[:16])
+    w = m.get_weights()
+    assert [a.shape for a in w] == [(8, 4), (8,), (2, 8), (2,)]
+    m2 = _model()
+    m2.set_weights(w)
+    assert np.allclose(m2.predict(x), p, atol=1e-6)
+    with pytest.raises(ValueError, match="expects 4 arrays"):
+        m2.set_weights(w[:2])
+    with pytest.raises(ValueError, match="shape mismatch"):
+        m2.set_weights([w[0].T] + w[1:])
+    m.save_weights(str(tmp_path / "w.pt"))
+    m3 = _model()
+    m3.load_weights(str(tmp_path / "w.pt"))
+    assert np.allclose(m3.predict(x), p, atol=1e-6)
+    lines = []
+    m.summary(print_fn=lines.append)
+    assert "dense (Dense)" in lines[0] and "dense_1 (Dense)" in lines[0] and "Total params: 58" in lines[0]
+    assert m.output_shape == (None, 2) and m.count_params() == 58
+    with pytest.raises(RuntimeError, match="after the model was built"):
+        m.add(keras.layers.Dense(1))
+
+
+def test_from_torch_wraps_an_arbitrary_module_and_errors_are_explicit():
+    net = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.Tanh(), torch.nn.Linear(6, 2))
+    m = keras.Model.from_torch(net, input_shape=(4,))
+    m.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True), optimizer="adam")
+    m._device = torch.device("cpu")
+    x, y = _xy()
+    h = m.fit(x, y, batch_size=16, epochs=4, verbose=0)
+    assert h.history["loss"][-1] < h.history["loss"][0]
+    with pytest.raises(ValueError, match="no layers"):
+        keras.Sequential().build()
+    with pytest.raises(ValueError, match="input_shape"):
+        keras.Sequential([keras.layers.Dense(2)]).build()
+    uncompiled = keras.Sequential([keras.layers.Dense(2, input_shape=(4,))])
+    with pytest.raises(RuntimeError, match="compile"):
+        uncompiled.fit(x, y, verbose=0)
+    with pytest.raises(ValueError, match="unknown optimizer"):
+        uncompiled.compile(optimizer="rmsprop-like", loss="mse")
+    with pytest.raises(TypeError, match="unexpected arguments"):
+        keras.layers.Dense(2, kernel_regularizer="l2")

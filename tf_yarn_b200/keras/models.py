@@ -525,11 +525,16 @@ class Model:
 
     def set_weights(self, weights: Sequence[np.ndarray]) -> None:
         self.build()
-        state = self.net.state_dict()
-        for (k, v), w in zip(state.items(), weights):
-            v.copy_(torch.as_tensor(w).to(v.dtype))
-        if isinstance(self._engine, GraphTrainEngine):
+        if isinstance(self._engine, GraphTrainEngine):     # the fp32 master copies live in the engine's shards
             raise RuntimeError("set_weights after training started on GPU: use load_weights on a fresh model")
+        state = self.net.state_dict()
+        if len(weights) != len(state):
+            raise ValueError(f"set_weights expects {len(state)} arrays, got {len(weights)}")
+        for (k, v), w in zip(state.items(), weights):
+            w = torch.as_tensor(w)
+            if tuple(w.shape) != tuple(v.shape):
+                raise ValueError(f"shape mismatch for {k}: {tuple(w.shape)} vs {tuple(v.shape)}")
+            v.copy_(w.to(v.dtype))
 
     def _fp32_state(self) -> Dict[str, torch.Tensor]:
         """Full-precision state dict (fp32 master weights when training on B200 in bf16)."""
