@@ -8,6 +8,7 @@ estimator is the BASELINE config that exercises the parameter-server path.
 """
 from __future__ import annotations
 
+import math
 from typing import Any, Callable, Dict, Optional, Sequence
 
 import torch
@@ -18,6 +19,7 @@ from tf_yarn_b200.estimator import feature_column as fc
 from tf_yarn_b200.estimator.config import RunConfig
 from tf_yarn_b200.estimator.estimator import Estimator
 from tf_yarn_b200.estimator.spec import EstimatorSpec
+from tf_yarn_b200.keras import optimizers as kopt
 
 
 def _classification_loss(n_classes: int) -> Callable:
@@ -94,9 +96,31 @@ class _WideDeepNet(nn.Module):
         return out
 
 
+def _tf_default(opt, tower: str, n_columns: int, combined: bool):
+    """An optimizer NAME gets the learning rate TF's canned estimators give it (tensorflow_estimator canned/dnn.py
+    ``_LEARNING_RATE = 0.05``, linear.py ``min(0.2, 1/sqrt(n_columns))``, dnn_linear_combined.py 0.001 / ``min(0.005,
+    1/sqrt(n_linear_columns))``) instead of the Keras class default (0.001); optimizer objects and callables pass
+    through untouched."""
+    if not isinstance(opt, str):
+        return opt
+    name = opt.lower()
+    per_columns = 1.0 / math.sqrt(max(n_columns, 1))
+    if tower == "dnn" and name == "adagrad":
+        return kopt.Adagrad(0.001 if combined else 0.05)
+    if tower == "linear" and name == "ftrl":
+        return kopt.Ftrl(min(0.005 if combined else 0.2, per_columns))
+    return opt
+
+
 def _canned_model_fn(linear_columns, dnn_columns, hidden_units, n_classes, optimizer, dropout=None,
                      linear_optimizer=None):
     n_out = 1 if n_classes == 2 else n_classes
+    combined = bool(linear_columns) and bool(dnn_columns)
+    if dnn_columns:
+        optimizer = _tf_default(optimizer, "dnn", len(dnn_columns), combined)
+        linear_optimizer = _tf_default(linear_optimizer, "linear", len(linear_columns), combined)
+    else:                                   # linear-only model: `optimizer` IS the linear optimizer
+        optimizer = _tf_default(optimizer, "linear", len(linear_columns), False)
 
     def model_fn(features, labels, mode, params=None, config=None):
         net = _WideDeepNet(linear_columns, dnn_columns, hidden_units, n_out, dropout=dropout)
