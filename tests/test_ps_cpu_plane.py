@@ -1,0 +1,69 @@
+"""Shared-memory parameter-server plane (estimator/ps.py) in process: the update applied on the ps copy by `push`
+must be the optimizer's update -- checked against torch.optim on the same gradient sequence for every optimizer a
+variable can carry (what TF's ps runs as ApplyGradientDescent / ApplyAdagrad / ApplyAdam / ApplyFtrl; reference:
+tf_yarn/tensorflow/tasks/tf_task_common.py:46-50)."""
+import pytest
+import torch
+
+from tf_yarn_b200 import keras
+from tf_yarn_b200.estimator import ps
+
+
+def _connection(tmp_path, net, desc, n_ps=2, by_name=None):
+    named = ps._named_trainables(net)
+    layout = ps.make_layout(named, n_ps, desc, by_name)
+    shards = [ps.ShmShard(str(tmp_path / f"shard{i}"), layout.shard_elems[i], create=True) for i in range(n_ps)]
+    for s in shards:
+        s.data.zero_()
+    conn = ps.WorkerConnection(layout, shards, [n for n, _ in named])
+    with torch.no_grad():
+        for i, (_, p) in enumerate(named):
+            conn._region(i).copy_(p.detach().reshape(-1))
+            if layout.kinds[i] in ("adagrad", "ftrl"):
+                conn._region(i, 1).fill_(layout.hypers[i]["init_s1"])
+    shards[0].set_global_step(0)
+    return conn, shards
+
+
+@pytest.mark.parametrize("desc", [keras.optimizers.SGD(0.1), keras.optimizers.Adagrad(0.1), keras.optimizers.Adam(0.01),
+                                  keras.optimizers.Adadelta(1.0),
+                                  keras.optimizers.Ftrl(0.1, l1_regularization_strength=0.001)],
+                         ids=["sgd", "adagrad", "adam", "adadelta", "ftrl"])
+def test_push_applies_the_optimizers_update(tmp_path, desc):
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3))
+    ref.load_state_dict(net.state_dict())
+    conn, shards = _connection(tmp_path, net, desc)
+    opt = desc.to_torch(ref.parameters())
+    g = torch.Generator().manual_seed(1)
+    for _ in range(6):
+        x, y = torch.randn(16, 5, generator=g), torch.randint(0, 3, (16,), generator=g)
+        conn.pull(net)
+        net.zero_grad()
+        torch.nn.functional.cross_entropy(net(x), y).backward()
+        conn.push(net)
+        conn.increment_global_step()                       # what Estimator.train does after every step
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(ref(x), y).backward()
+        opt.step()
+    conn.pull(net)
+    for (n, a), (_, b) in zip(net.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(a, b, atol=2e-6, rtol=1e-5), (n, (a - b).abs().max().item())
+    assert conn.global_step() == 6 and set(conn.state_dict_from_ps(net)) == set(ref.state_dict())
+    for s in shards:
+        s.unlink()
+
+
+def test_per_variable_optimizers_and_round_robin_placement(tmp_path):
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    by_name = {"0.weight": keras.optimizers.Ftrl(0.05), "0.bias": keras.optimizers.Ftrl(0.05)}
+    conn, shards = _connection(tmp_path, net, keras.optimizers.Adagrad(0.1), n_ps=3, by_name=by_name)
+    lay = conn.layout
+    assert lay.kinds == ["ftrl", "ftrl", "adagrad", "adagrad"] and lay.owner == [0, 1, 2, 0]
+    assert lay.var_slots == [2, 2, 1, 1] and lay.shard_elems == [16 * 3 + 8 * 2, 8 * 3, 8 * 2]
+    again = ps.Layout.from_json(lay.to_json())
+    assert again.offset == lay.offset and again.hypers == lay.hypers
+    assert shards[0].add_global_step(5) == 5 and shards[0].global_step() == 5
+    for s in shards:
+        s.unlink()

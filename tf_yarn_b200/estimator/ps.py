@@ -197,11 +197,11 @@ class WorkerConnection:
                     upd = g * (dx + eps).sqrt() / (sq + eps).sqrt()
                     dx.mul_(p1).addcmul_(upd, upd, value=1 - p1)
                     w.add_(upd, alpha=-lr)
-                else:  # adam: per-worker step count for the bias correction (stale-gradient tolerant)
+                else:  # adam: bias correction from the shared global step, like the HBM plane (ps_hbm.refresh_adam_scale)
                     m, v = self._region(i, 1), self._region(i, 2)
                     m.mul_(p1).add_(g, alpha=1 - p1)
                     v.mul_(p2).addcmul_(g, g, value=1 - p2)
-                    t = max(self.global_step(), 1)
+                    t = max(self.global_step(), 0) + 1     # the step being applied: incremented AFTER the push
                     bc1, bc2 = 1 - p1 ** t, 1 - p2 ** t
                     w.addcdiv_(m, (v / bc2).sqrt().add_(eps), value=-lr / bc1)
 
