@@ -7,7 +7,7 @@ import pytest
 
 from tf_yarn_b200 import client, constants
 from tf_yarn_b200.client import ContainerLogStatus, RunFailed, _handle_events, get_safe_experiment_fn, run_on_yarn
-from tf_yarn_b200.topologies import ContainerKey, TaskSpec
+from tf_yarn_b200.topologies import ContainerKey, NodeLabel, TaskSpec
 
 from fakes import FakeClient
 
@@ -146,3 +146,43 @@ def test_aggregate_events_collects_task_stages():
 
 def test_run_failed_is_an_exception():
     assert issubclass(RunFailed, Exception)
+
+
+def test_services_carry_the_task_environment_and_scripts(monkeypatch):
+    """What each role is started with: retry index, PYTHONPATH for shipped files, TensorBoard knobs from the TaskSpec,
+    the pre-script hook ahead of the task command, the custom task module for trainers only
+    (reference: tf_yarn/client.py:108-151, _env.py:6-24)."""
+    captured = {}
+
+    class StubApp:
+        def __init__(self):
+            from tf_yarn_b200.kv import InMemoryKV
+            self.kv = InMemoryKV()
+
+    class StubClient:
+        def submit_and_connect(self, spec):
+            captured["spec"] = spec
+            return StubApp()
+
+    specs = {"chief": TaskSpec("1 GiB", 2, label=NodeLabel.GPU), "worker": TaskSpec("1 GiB", 2, instances=3),
+             "tensorboard": TaskSpec("512 MiB", 1, tb_model_dir="/models/m", tb_extra_args="--reload_interval 5",
+                                     tb_termination_timeout_seconds=7)}
+    cluster = client._setup_local_cluster(
+        specs, custom_task_module="my_pkg.my_task", local_client=StubClient(), files={"my_pkg": "/src/my_pkg"},
+        env={"LD_LIBRARY_PATH": "/usr/lib", "FOO": "bar"}, n_try=2, pre_script_hook="source env.sh",
+        cuda_runtime_hdfs_path="viewfs://root/cuda.tar.gz", name="job", queue="ml")
+    cluster.event_listener.stop_event.set()
+    app_spec = captured["spec"]
+    assert app_spec.name == "job" and app_spec.queue == "ml" and set(app_spec.services) == set(specs)
+    chief, worker, tb = (app_spec.services[k] for k in ("chief", "worker", "tensorboard"))
+    assert chief.env["TF_YARN_N_TRY"] == chief.env["TFY_N_TRY"] == "2" and chief.env["FOO"] == "bar"
+    assert chief.env["PYTHONPATH"].startswith(".:") and chief.files == {"my_pkg": "/src/my_pkg"}
+    assert (worker.instances, worker.nb_proc, worker.vcores, worker.memory) == (3, 1, 2, 1024)
+    assert chief.label == NodeLabel.GPU and worker.label == NodeLabel.CPU
+    assert chief.script.splitlines()[:2] == ["set -e", "source env.sh"]
+    assert chief.script.splitlines()[-1].startswith("exec ") and "my_pkg.my_task" in chief.script
+    assert "my_pkg.my_task" not in tb.script and "_tensorboard_task" in tb.script
+    assert tb.env["TB_MODEL_DIR"] == "/models/m" and tb.env["TB_EXTRA_ARGS"] == "--reload_interval 5"
+    assert tb.env["TB_TERMINATION_TIMEOUT_SECONDS"] == "7" and "TB_MODEL_DIR" not in chief.env
+    assert cluster.tasks == [("chief", 1, 1), ("worker", 3, 1), ("tensorboard", 1, 1)]
+    assert client._default_acls_all_access() == {"enable": True, "ui_users": ["*"], "view_users": ["*"]}
