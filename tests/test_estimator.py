@@ -288,3 +288,25 @@ def test_per_tower_optimizer_state_survives_a_checkpoint(tmp_path):
     # accumulators grew past their initial value: the restored state is the trained one, not a fresh optimizer
     flat = [v for st in restored["multi"] for s in st["state"].values() for v in s.values() if torch.is_tensor(v)]
     assert flat and any(float(v.abs().max()) > 0.1 for v in flat)
+
+
+def test_continuous_eval_stops_on_idle_timeout_and_on_stop_condition(tmp_path):
+    """No checkpoint ever appears: the evaluator gives up after its idle timeout, or as soon as the stop condition
+    (every trainer reported `stop`) holds (reference: tf_yarn/tensorflow/tasks/evaluator_task.py:18-25,83-127)."""
+    import time
+    from tf_yarn_b200.estimator import training
+
+    class Idle:
+        model_dir = str(tmp_path)
+
+        def evaluate(self, *a, **k):
+            raise AssertionError("nothing to evaluate")
+
+    spec = est.EvalSpec(lambda: iter(()), steps=1, start_delay_secs=0, throttle_secs=0)
+    t0 = time.time()
+    assert training.continuous_eval(Idle(), est.TrainSpec(lambda: iter(()), max_steps=10), spec, timeout_secs=0.3) is None
+    assert 0.25 < time.time() - t0 < 5.0
+    calls = []
+    assert training.continuous_eval(Idle(), est.TrainSpec(lambda: iter(()), max_steps=10), spec, timeout_secs=60,
+                                    stop_cond=lambda: calls.append(1) or len(calls) >= 3) is None
+    assert len(calls) == 3
