@@ -103,3 +103,43 @@ def test_from_torch_wraps_an_arbitrary_module_and_errors_are_explicit():
         uncompiled.compile(optimizer="rmsprop-like", loss="mse")
     with pytest.raises(TypeError, match="unexpected arguments"):
         keras.layers.Dense(2, kernel_regularizer="l2")
+
+
+def test_load_model_resumes_with_the_saved_optimizer_state(tmp_path, caplog):
+    """save() -> load_model() -> fit() continues exactly like an uninterrupted run (Adam moments and step count are
+    part of the checkpoint), which is what the reference's evaluator / resume flows rely on with tf.keras."""
+    x, y = _xy(64)
+
+    def fresh():
+        torch.manual_seed(5)
+        m = keras.Sequential([keras.layers.Dense(6, activation="tanh", input_shape=(4,)), keras.layers.Dense(2)])
+        m.compile(loss=keras.losses.SparseCategoricalCrossentropy(from_logits=True), optimizer=keras.optimizers.Adam(0.05))
+        m._device = torch.device("cpu")
+        return m
+
+    straight = fresh()
+    straight.fit(x, y, batch_size=16, epochs=3, shuffle=False, verbose=0)
+    first = fresh()
+    first.fit(x, y, batch_size=16, epochs=2, shuffle=False, verbose=0)
+    path = str(tmp_path / "ckpt-2")
+    first.save(path)
+    resumed = keras.models.load_model(path)
+    resumed._device = torch.device("cpu")
+    assert resumed._pending_engine_state["kind"] == "eager"
+    resumed.fit(x, y, batch_size=16, epochs=1, shuffle=False, verbose=0)
+    for a, b in zip(resumed.get_weights(), straight.get_weights()):
+        assert np.allclose(a, b, atol=1e-6)
+    assert resumed._pending_engine_state is None
+
+    weights_only = keras.models.load_model(path)                 # without the optimizer state the run diverges
+    weights_only._device = torch.device("cpu")
+    weights_only._pending_engine_state = None
+    weights_only.fit(x, y, batch_size=16, epochs=1, shuffle=False, verbose=0)
+    assert not all(np.allclose(a, b, atol=1e-6) for a, b in zip(weights_only.get_weights(), straight.get_weights()))
+
+    foreign = keras.models.load_model(path)
+    foreign._device = torch.device("cpu")
+    foreign._pending_engine_state = {"kind": "fused", "master": torch.zeros(3)}
+    with caplog.at_level("WARNING"):
+        foreign.fit(x, y, batch_size=16, epochs=1, shuffle=False, verbose=0)
+    assert "optimizer starts fresh" in caplog.text

@@ -151,6 +151,7 @@ class Model:
         self.history = None
         self._watchdog = None             # utils.watchdog.StepWatchdog while fit() runs
         self._pending_broadcast_root: Optional[int] = None
+        self._pending_engine_state: Optional[dict] = None    # optimizer state of a loaded checkpoint (load_model)
         for layer in layers or []:
             self.add(layer)
 
@@ -251,9 +252,31 @@ class Model:
                 hvd.ensure_cpu_group()
             self._engine = EagerTrainEngine(self.net, self._loss_fn, self.optimizer, self._metric_fns(),
                                             self._device, distributed)
+        self._restore_engine_state()
         if self._pending_broadcast_root is not None:
             self._engine.broadcast_variables(self._pending_broadcast_root)
             self._pending_broadcast_root = None
+
+    def _restore_engine_state(self) -> None:
+        """``load_model`` keeps the saved optimizer state (moments, accumulators, step count) until the train engine
+        exists; training then resumes where the checkpoint left off, as with ``tf.keras.models.load_model``.  A state
+        written by a different engine / world size is skipped with a warning (the weights are already restored)."""
+        state, self._pending_engine_state = self._pending_engine_state, None
+        if not state:
+            return
+        want = "eager" if isinstance(self._engine, EagerTrainEngine) else "fused"
+        if state.get("kind") != want:
+            logger.warning("checkpoint optimizer state is of kind %r, the engine needs %r: optimizer starts fresh",
+                           state.get("kind"), want)
+            return
+        try:
+            if self._device.type == "cuda":
+                torch.cuda.synchronize(self._device)
+            self._engine.load_state_dict(state)
+            if self._device.type == "cuda":
+                torch.cuda.synchronize(self._device)
+        except Exception as exc:  # noqa: BLE001  (shape / world-size mismatch: keep training possible)
+            logger.warning("could not restore the optimizer state of the checkpoint (%s): optimizer starts fresh", exc)
 
     def to(self, device) -> "Model":
         self._device = torch.device(device)
@@ -607,6 +630,7 @@ def load_model(filepath: str, compile: bool = True) -> Model:
     if compile and comp.get("loss") and comp.get("optimizer"):
         model.compile(optimizer=opt_mod.from_config(comp["optimizer"]), loss=loss_mod.deserialize(comp["loss"]),
                       metrics=comp.get("metrics") or [])
+        model._pending_engine_state = payload.get("optimizer_state")
     return model
 
 
