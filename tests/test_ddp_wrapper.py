@@ -110,3 +110,39 @@ def test_channels_last_parameters_get_channels_last_gradient_views():
         assert torch.allclose(p.grad, q.grad, atol=1e-5)
         b, i = ddp._param_bucket[id(p)]
         assert p.grad.untyped_storage().data_ptr() == b.flat.untyped_storage().data_ptr()
+
+
+def test_fused_optimizer_state_is_sharded_and_foreign_shards_are_not_adopted(caplog):
+    """Rank 0 saves ITS shard (the reference saves on rank 0 only).  Rank 0 restores it verbatim; another rank must
+    not adopt rank 0's master weights: it rebuilds its own shard from the restored parameters."""
+    from types import SimpleNamespace
+    import torch
+    from tf_yarn_b200.parallel.ddp import _FusedOptimizer
+    from tf_yarn_b200.parallel.optspec import OptimizerSpec
+
+    def make(rank):
+        shard_n = 8
+        pflat = torch.arange(16, dtype=torch.float32)                      # the (restored) parameters, both shards
+        b = SimpleNamespace(params=[], shard_n=shard_n, pflat=pflat, master=torch.zeros(shard_n),
+                            s1=torch.zeros(shard_n), s2=torch.zeros(shard_n), hyper=torch.zeros(64, dtype=torch.uint8))
+        ddp = SimpleNamespace(_buckets=[b], comm=SimpleNamespace(rank=rank, world=2))
+        return _FusedOptimizer(ddp, OptimizerSpec.adam(1e-3)), b
+
+    saver, sb = make(0)
+    sb.master.copy_(torch.arange(8, dtype=torch.float32) + 0.25)           # fp32 master carries more than the params
+    sb.s1.fill_(0.5), sb.s2.fill_(0.125)
+    sb.hyper[24:28].copy_(torch.tensor([7], dtype=torch.int32).view(torch.uint8))
+    state = saver.state_dict()
+    assert state["buckets"][0]["rank"] == 0 and state["buckets"][0]["step"] == 7
+
+    same, b0 = make(0)
+    same.load_state_dict(state)
+    assert torch.equal(b0.master, sb.master) and float(b0.s1[0]) == 0.5 and float(b0.s2[0]) == 0.125
+    assert int(b0.hyper[24:28].view(torch.int32).item()) == 7
+
+    other, b1 = make(1)
+    with caplog.at_level("WARNING"):
+        other.load_state_dict(state)
+    assert torch.equal(b1.master, torch.arange(8, 16, dtype=torch.float32))     # ITS slice of the parameters
+    assert float(b1.s1.abs().max()) == 0.0 and float(b1.s2.abs().max()) == 0.0
+    assert int(b1.hyper[24:28].view(torch.int32).item()) == 7 and "another rank's shard" in caplog.text

@@ -358,9 +358,29 @@ class _FusedOptimizer:
         return out
 
     def load_state_dict(self, state: dict) -> None:
+        """Restore what :meth:`state_dict` saved.  The state is SHARDED (each rank owns 1/world of the fp32 master
+        weights and moments) while the reference's flow saves on rank 0 only (tf_yarn/pytorch/model_ckpt.py:55-72):
+        a rank that is handed another rank's shard rebuilds its fp32 master from the parameters the model checkpoint
+        has just restored and restarts its moments, instead of adopting foreign values."""
+        comm = self._ddp.comm
+        me = comm.rank if comm.world > 1 else 0
+        foreign = False
         for b, st in zip(self._ddp._buckets, state["buckets"]):
-            b.master.copy_(st["master"]); b.s1.copy_(st["s1"]); b.s2.copy_(st["s2"])
+            if int(st.get("rank", 0)) == me and st["master"].numel() == b.master.numel():
+                b.master.copy_(st["master"])
+                b.s1.copy_(st["s1"])
+                b.s2.copy_(st["s2"])
+            else:
+                foreign = True
+                b.master.copy_(b.pflat[me * b.shard_n:(me + 1) * b.shard_n].float())
+                b.s1.fill_(self.spec.init_s1)
+                b.s2.zero_()
             b.hyper[24:28].copy_(torch.tensor([st["step"]], dtype=torch.int32).view(torch.uint8))
+        if foreign:
+            import logging
+            logging.getLogger(__name__).warning(
+                "rank %d: the optimizer checkpoint holds another rank's shard; fp32 master rebuilt from the restored "
+                "parameters, moments restart on this rank", me)
 
 
 def wrap_model(model: nn.Module, device, ddp_kwargs: Optional[dict] = None, comm: Optional[Communicator] = None):
