@@ -143,3 +143,32 @@ def test_load_model_resumes_with_the_saved_optimizer_state(tmp_path, caplog):
     with caplog.at_level("WARNING"):
         foreign.fit(x, y, batch_size=16, epochs=1, shuffle=False, verbose=0)
     assert "optimizer starts fresh" in caplog.text
+
+
+def test_single_rank_readers_never_start_a_collective_when_state_is_sharded(tmp_path):
+    """On several GPUs the fp32 master / optimizer state is sharded; ModelCheckpoint runs on the chief ALONE, so
+    save() / get_weights() must not call the engine's gathering (collective) paths: they read the replicated
+    parameters and leave the optimizer state out."""
+    from types import SimpleNamespace
+    from tf_yarn_b200.keras import models as kmodels
+    m = _model()
+    m.build()
+
+    class Boom:
+        def __getattr__(self, name):
+            raise AssertionError(f"collective path touched: {name}")
+
+    eng = kmodels.GraphTrainEngine.__new__(kmodels.GraphTrainEngine)
+    eng.comm = SimpleNamespace(world=8)
+    eng.fused = Boom()                       # gather_state / master_tensors would go through here
+    m._engine = eng
+    assert m._sharded_across_ranks()
+    w = m.get_weights()
+    assert [a.shape for a in w] == [(8, 4), (8,), (2, 8), (2,)]
+    path = str(tmp_path / "ck")
+    m.save(path)
+    import pickle
+    payload = pickle.load(open(path, "rb"))
+    assert payload["optimizer_state"] is None and set(payload["weights"]) == set(m.net.state_dict())
+    eng.comm = SimpleNamespace(world=1)
+    assert not m._sharded_across_ranks()

@@ -563,7 +563,7 @@ class Model:
         """Full-precision state dict (fp32 master weights when training on B200 in bf16)."""
         self.build()
         state = {k: v.detach().float().cpu().clone() for k, v in self.net.state_dict().items()}
-        if isinstance(self._engine, GraphTrainEngine):
+        if isinstance(self._engine, GraphTrainEngine) and not self._sharded_across_ranks():
             names = self._param_names()
             for name, t in zip(names, self._engine.master_tensors()):
                 state[name] = t.detach().float().cpu().contiguous()
@@ -576,8 +576,21 @@ class Model:
                 "input_shape": list(self.layers[0].input_shape_) if self.built else
                 (list(self.layers[0]._declared_input_shape) if self.layers[0]._declared_input_shape else None)}
 
+    def _sharded_across_ranks(self) -> bool:
+        """True when the fp32 master weights / optimizer state are split over several GPUs.  Collecting them is a
+        COLLECTIVE (every rank would have to call it), while checkpoints are written by one rank alone -- the
+        all-reduce task strips ``ModelCheckpoint`` from every rank but the chief, as the reference does
+        (tf_yarn/tensorflow/tasks/gloo_allred_task.py:79-84) -- so single-rank readers use the replicated compute
+        parameters instead (bf16-rounded on B200) and leave the optimizer state out."""
+        comm = getattr(self._engine, "comm", None)
+        return comm is not None and getattr(comm, "world", 1) > 1
+
     def save(self, filepath: str, include_optimizer: bool = True) -> None:
         """Atomically write config + fp32 weights (+ optimizer state) to ``filepath``."""
+        if self._engine is not None and self._sharded_across_ranks() and not getattr(self, "_warned_sharded", False):
+            self._warned_sharded = True
+            logger.info("multi-rank training: the checkpoint holds this rank's replicated parameters (compute "
+                        "precision) and no optimizer state; gathering the sharded fp32 state would be a collective")
         payload = {
             "format": "tf_yarn_b200.keras/1",
             "config": self.get_config(),
@@ -585,8 +598,8 @@ class Model:
             "compile": {"loss": loss_mod.serialize(self.loss),
                         "optimizer": self.optimizer.get_config() if self.optimizer is not None else None,
                         "metrics": [m for m in self._metrics_spec if isinstance(m, str)]},
-            "optimizer_state": (self._engine.state_dict() if (include_optimizer and self._engine is not None)
-                                else None),
+            "optimizer_state": (self._engine.state_dict() if (include_optimizer and self._engine is not None
+                                                              and not self._sharded_across_ranks()) else None),
         }
         os.makedirs(os.path.dirname(os.path.abspath(filepath)), exist_ok=True)
         tmp = f"{filepath}.tmp{os.getpid()}"
