@@ -150,7 +150,7 @@ def test_single_rank_readers_never_start_a_collective_when_state_is_sharded(tmp_
     save() / get_weights() must not call the engine's gathering (collective) paths: they read the replicated
     parameters and leave the optimizer state out."""
     from types import SimpleNamespace
-    from tf_yarn_b200.keras import models as kmodels
+    from tf_yarn_b200.keras.engine import GraphTrainEngine
     m = _model()
     m.build()
 
@@ -158,7 +158,7 @@ def test_single_rank_readers_never_start_a_collective_when_state_is_sharded(tmp_
         def __getattr__(self, name):
             raise AssertionError(f"collective path touched: {name}")
 
-    eng = kmodels.GraphTrainEngine.__new__(kmodels.GraphTrainEngine)
+    eng = GraphTrainEngine.__new__(GraphTrainEngine)
     eng.comm = SimpleNamespace(world=8)
     eng.fused = Boom()                       # gather_state / master_tensors would go through here
     m._engine = eng
