@@ -77,3 +77,59 @@ def test_in_memory_kv():
     assert store["k"] == b"v" and store.wait("k") == b"v" and store.keys() == ["k"]
     with pytest.raises(TimeoutError):
         store.wait("x", timeout=0.1)
+
+
+def test_wait_connections_do_not_leak_descriptors(server):
+    """Every `wait` is its own connection (a parked WAIT must not block puts); a barrier over W ranks is ~W waits per
+    rank, so the server has to release the descriptor of each finished one (round-1 review: it only shut them down)."""
+    import os
+    c = kv.KVClient(server.address)
+    c["ready"] = b"1"
+    for _ in range(20):
+        c.wait("ready")
+    time.sleep(0.3)
+    before = len(os.listdir("/proc/self/fd"))
+    for _ in range(400):
+        assert c.wait("ready") == b"1"
+    time.sleep(0.5)
+    after = len(os.listdir("/proc/self/fd"))
+    assert after - before < 20, (before, after)
+
+
+def test_many_clients_barrier(server):
+    """32 threads rendezvous through put + wait of each other's keys, the pattern of the init / stop barriers."""
+    n = 32
+    errors = []
+
+    def member(i):
+        try:
+            c = kv.KVClient(server.address)
+            c[f"m:{i}/init"] = str(i)
+            for j in range(n):
+                assert c.wait(f"m:{j}/init", timeout=30) == str(j).encode()
+            c.close()
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+    threads = [threading.Thread(target=member, args=(i,)) for i in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert not errors and not any(t.is_alive() for t in threads)
+    assert len(kv.KVClient(server.address).keys("m:")) == n
+
+
+def test_unicode_keys_and_reconnect_after_the_connection_dropped(server):
+    c = kv.KVClient(server.address)
+    c["tâche:0/état"] = "prêt"
+    assert c["tâche:0/état"] == "prêt".encode() and c.keys("tâche") == ["tâche:0/état"]
+    c._sock.close()                                    # the next request notices and reconnects once
+    assert c.get("tâche:0/état") == "prêt".encode()
+    with pytest.raises(RuntimeError, match="no KV address"):
+        import os
+        old = os.environ.pop(kv.KV_ADDR_ENV, None)
+        try:
+            kv.KVClient()
+        finally:
+            if old is not None:
+                os.environ[kv.KV_ADDR_ENV] = old
