@@ -11,15 +11,15 @@ from tf_yarn_b200.utils import watchdog
 
 def test_fires_without_heartbeats_and_not_with_them():
     fired = []
-    wd = watchdog.StepWatchdog(0.2, "loop", action=lambda what, idle: fired.append((what, idle))).start()
+    wd = watchdog.StepWatchdog(0.6, "loop", action=lambda what, idle: fired.append((what, idle))).start()
     t0 = time.time()
-    while time.time() - t0 < 0.5:                 # beating: never fires
+    while time.time() - t0 < 1.0:                 # beating: never fires
         wd.beat()
         time.sleep(0.02)
     assert not fired and not wd.fired
-    time.sleep(0.6)                               # silent: fires once
+    time.sleep(1.5)                               # silent: fires once
     wd.close()
-    assert len(fired) == 1 and fired[0][0] == "loop" and fired[0][1] > 0.2 and wd.fired
+    assert len(fired) == 1 and fired[0][0] == "loop" and fired[0][1] > 0.6 and wd.fired
 
 
 def test_zero_timeout_is_inert_and_env_overrides_the_default(monkeypatch):
