@@ -310,3 +310,28 @@ def test_continuous_eval_stops_on_idle_timeout_and_on_stop_condition(tmp_path):
     assert training.continuous_eval(Idle(), est.TrainSpec(lambda: iter(()), max_steps=10), spec, timeout_secs=60,
                                     stop_cond=lambda: calls.append(1) or len(calls) >= 3) is None
     assert len(calls) == 3
+
+
+def test_exports_in_the_same_second_get_distinct_directories_and_predict_modes(tmp_path):
+    import torch
+    e = _classifier(tmp_path / "m") if "_classifier" in globals() else None
+    if e is None:
+        from tf_yarn_b200.estimator import feature_column as fc
+        e = est.LinearClassifier([fc.numeric_column("x", shape=(6,))], model_dir=str(tmp_path / "m"), n_classes=3,
+                                 config=est.RunConfig(save_checkpoints_steps=5))
+    g = torch.Generator().manual_seed(0)
+    xs = torch.randn(40, 6, generator=g)
+    ys = torch.randint(0, 3, (40,), generator=g)
+
+    def input_fn():
+        from tf_yarn_b200.data import Dataset
+        return Dataset.from_tensor_slices(({"x": xs}, ys)).batch(8)
+    e.train(input_fn, max_steps=5)
+    base = str(tmp_path / "export")
+    outs = [e.export_saved_model(base) for _ in range(3)]
+    assert len(set(outs)) == 3 and sorted(outs) == outs
+    assert all(os.path.exists(os.path.join(o, "saved_model.pt")) for o in outs)
+    single = list(e.predict(input_fn))
+    assert len(single) == 40 and single[0]["probabilities"].shape == (3,)
+    batched = list(e.predict(input_fn, yield_single_examples=False))
+    assert len(batched) == 5 and tuple(batched[0]["probabilities"].shape) == (8, 3)

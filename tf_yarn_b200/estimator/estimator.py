@@ -573,8 +573,14 @@ class Estimator:
             raise RuntimeError("export needs a built network: call train() or evaluate() first")
         if path:
             self._restore(path, with_optimizer=False)
-        out = os.path.join(export_dir_base, str(int(time.time())))
-        os.makedirs(out, exist_ok=True)
+        stamp = int(time.time())
+        while True:                     # like TF: two exports within one second get distinct, increasing directories
+            out = os.path.join(export_dir_base, str(stamp))
+            try:
+                os.makedirs(out)
+                break
+            except FileExistsError:
+                stamp += 1
         tmp = os.path.join(out, f"saved_model.pt.tmp{os.getpid()}")
         import cloudpickle
         with open(tmp, "wb") as f:
