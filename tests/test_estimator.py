@@ -335,3 +335,40 @@ def test_exports_in_the_same_second_get_distinct_directories_and_predict_modes(t
     assert len(single) == 40 and single[0]["probabilities"].shape == (3,)
     batched = list(e.predict(input_fn, yield_single_examples=False))
     assert len(batched) == 5 and tuple(batched[0]["probabilities"].shape) == (8, 3)
+
+
+def test_a_checkpoint_pruned_before_it_was_loaded_is_skipped_not_misreported(tmp_path):
+    """The chief prunes old checkpoints (keep_checkpoint_max) while the evaluator works through its list: a checkpoint
+    that vanished must raise from evaluate(checkpoint_path=...) and be skipped by the evaluator loop, never be
+    'evaluated' with the weights of another step."""
+    import torch
+    from tf_yarn_b200.estimator import checkpoint as ckpt
+    from tf_yarn_b200.estimator import feature_column as fc
+    from tf_yarn_b200.estimator import training
+    e = est.LinearClassifier([fc.numeric_column("x", shape=(3,))], model_dir=str(tmp_path), n_classes=2,
+                             config=est.RunConfig(save_checkpoints_steps=2, keep_checkpoint_max=10))
+    g = torch.Generator().manual_seed(0)
+    xs, ys = torch.randn(32, 3, generator=g), torch.randint(0, 2, (32,), generator=g)
+
+    def input_fn():
+        from tf_yarn_b200.data import Dataset
+        return Dataset.from_tensor_slices(({"x": xs}, ys)).batch(8).repeat()
+    e.train(input_fn, max_steps=6)
+    paths = ckpt.get_checkpoint_state(str(tmp_path)).all_model_checkpoint_paths
+    assert [ckpt.step_of(p) for p in paths] == [0, 2, 4, 6]
+    with pytest.raises(FileNotFoundError):
+        e.evaluate(input_fn, steps=1, checkpoint_path=str(tmp_path / "model.ckpt-999"))
+
+    seen = []
+    real_evaluate = e.evaluate
+
+    def evaluate_and_prune(input_fn, steps=None, hooks=None, name=None, checkpoint_path=None):
+        if ckpt.step_of(checkpoint_path) == 0:           # while step 0 is evaluated the chief prunes step 2
+            os.remove(str(tmp_path / "model.ckpt-2"))
+        res = real_evaluate(input_fn, steps=steps, hooks=hooks, name=name, checkpoint_path=checkpoint_path)
+        seen.append(int(res["global_step"]))
+        return res
+    e.evaluate = evaluate_and_prune
+    last = training.continuous_eval(e, est.TrainSpec(input_fn, max_steps=6),
+                                    est.EvalSpec(input_fn, steps=1, start_delay_secs=0, throttle_secs=0), timeout_secs=30)
+    assert seen == [0, 4, 6] and int(last["global_step"]) == 6

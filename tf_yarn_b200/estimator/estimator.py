@@ -475,7 +475,10 @@ class Estimator:
         spec = self._build(features, labels, ModeKeys.EVAL)
         path = checkpoint_path or self.latest_checkpoint()
         if path:
-            self._restore(path, with_optimizer=False)
+            if not self._restore(path, with_optimizer=False) and checkpoint_path:
+                # an explicitly named checkpoint that vanished (the chief prunes old ones: keep_checkpoint_max) must
+                # not be "evaluated" with whatever weights the network happens to hold
+                raise FileNotFoundError(f"checkpoint {checkpoint_path} does not exist (pruned while waiting?)")
         elif self._ps is not None and self._network is not None:
             self._ps.pull(self._network)
         gs = self._global_step

@@ -47,8 +47,14 @@ def continuous_eval(estimator, train_spec: TrainSpec, eval_spec: EvalSpec, timeo
                 if ckpt.step_of(p) not in evaluated and os.path.exists(p)]
         for path in sorted(todo, key=ckpt.step_of):
             stamp = datetime.now()
-            last_result = estimator.evaluate(eval_spec.input_fn, steps=eval_spec.steps, hooks=eval_spec.hooks,
-                                             name=eval_spec.name, checkpoint_path=path)
+            try:
+                result = estimator.evaluate(eval_spec.input_fn, steps=eval_spec.steps, hooks=eval_spec.hooks,
+                                            name=eval_spec.name, checkpoint_path=path)
+            except FileNotFoundError:               # pruned by the chief between listing and loading: skip it
+                logger.info("checkpoint %s disappeared before it could be evaluated", path)
+                evaluated.add(ckpt.step_of(path))
+                continue
+            last_result = result
             evaluated.add(ckpt.step_of(path))
             gs = last_result.get(GraphKeys.GLOBAL_STEP) if last_result else None
             if train_spec.max_steps and gs is not None and gs >= train_spec.max_steps:
