@@ -146,3 +146,19 @@ def test_fused_optimizer_state_is_sharded_and_foreign_shards_are_not_adopted(cap
     assert torch.equal(b1.master, torch.arange(8, 16, dtype=torch.float32))     # ITS slice of the parameters
     assert float(b1.s1.abs().max()) == 0.0 and float(b1.s2.abs().max()) == 0.0
     assert int(b1.hyper[24:28].view(torch.int32).item()) == 7 and "another rank's shard" in caplog.text
+
+
+def test_fused_masters_follow_a_loaded_model_checkpoint():
+    """After module.load_state_dict(...) the fp32 master shards must be re-derived from the parameters: the fused
+    kernel writes parameters FROM the master, so a stale master would undo the load at the next step."""
+    from types import SimpleNamespace
+    import torch
+    from tf_yarn_b200.parallel.ddp import DistributedDataParallel
+    pflat = torch.arange(16, dtype=torch.bfloat16)
+    b = SimpleNamespace(shard_n=8, pflat=pflat, master=torch.full((8,), -1.0))
+    stub = SimpleNamespace(comm=SimpleNamespace(rank=1, world=2), _buckets=[b])
+    DistributedDataParallel._resync_fused_masters(stub)
+    assert b.master.dtype == torch.float32 and torch.equal(b.master, torch.arange(8, 16, dtype=torch.float32))
+    solo = SimpleNamespace(comm=SimpleNamespace(rank=0, world=1), _buckets=[b])
+    DistributedDataParallel._resync_fused_masters(solo)
+    assert torch.equal(b.master, torch.arange(0, 8, dtype=torch.float32))

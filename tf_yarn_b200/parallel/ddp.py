@@ -202,7 +202,17 @@ class DistributedDataParallel(nn.Module):
         if world > 1:
             comm.barrier()
         self._fused = _FusedOptimizer(self, spec)
+        # loading a model checkpoint writes the (replicated) parameters; the fp32 master shards the fused kernel
+        # updates FROM must follow, or the next step would overwrite the loaded weights with the old master
+        self.module.register_load_state_dict_post_hook(lambda _module, _keys: self._resync_fused_masters())
         return self._fused
+
+    def _resync_fused_masters(self) -> None:
+        """fp32 master shard of every bucket := this rank's slice of the current parameters."""
+        me = self.comm.rank if self.comm.world > 1 else 0
+        with torch.no_grad():
+            for b in self._buckets:
+                b.master.copy_(b.pflat[me * b.shard_n:(me + 1) * b.shard_n].float())
 
     def _sync_params_and_buffers(self) -> None:
         if self.comm.world == 1:
