@@ -614,6 +614,9 @@ class Model:
 
     def load_weights(self, filepath: str) -> None:
         self.build()
+        if isinstance(self._engine, GraphTrainEngine):     # same reason as set_weights: the fp32 master would go stale
+            raise RuntimeError("load_weights after training started on GPU: load into a fresh model (or use "
+                               "keras.models.load_model) before fit()")
         state = torch.load(filepath, map_location="cpu", weights_only=False)
         if isinstance(state, dict) and "weights" in state and "config" in state:
             state = state["weights"]
