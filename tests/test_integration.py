@@ -179,3 +179,22 @@ def test_keras_experiment_is_rejected_by_the_ps_task(tmp_path):
     with pytest.raises(RunFailed) as err:
         run_on_yarn(_keras_experiment(str(tmp_path / "m")), {"chief": TaskSpec("1 GiB", 1)})
     assert "KerasExperiment using parameter strategy is unsupported" in str(err.value)
+
+
+_ALL_EXAMPLES = os.environ.get("TFY_TEST_ALL_EXAMPLES") == "1"      # the other two take a minute more
+
+
+@pytest.mark.parametrize("example", ["mnist_cnn_allreduce", "bert_allreduce"] +
+                         (["wide_deep_ps", "resnet50_ddp"] if _ALL_EXAMPLES else []))
+def test_baseline_config_examples_run_end_to_end(example):
+    """The four BASELINE.json configurations as a user would launch them (toy sizes on CPU): all-reduce Keras with an
+    evaluator fed by `validation_data_fn=lambda: (x, y)`, the parameter-server Estimator, the PyTorch DDP experiment,
+    and BERT (dict inputs / outputs) with evaluator + TensorBoard side tasks."""
+    import subprocess
+    import sys
+    env = dict(os.environ, EXAMPLE_SMALL="1", EXAMPLE_EPOCHS="1", CUDA_VISIBLE_DEVICES="")
+    res = subprocess.run([sys.executable, "-m", f"tf_yarn_b200.examples.baseline.{example}"], env=env,
+                         capture_output=True, text=True, timeout=600,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert res.returncode == 0, (res.stdout + res.stderr)[-4000:]
+    assert "Metrics(" in res.stdout

@@ -172,3 +172,35 @@ def test_single_rank_readers_never_start_a_collective_when_state_is_sharded(tmp_
     assert payload["optimizer_state"] is None and set(payload["weights"]) == set(m.net.state_dict())
     eng.comm = SimpleNamespace(world=1)
     assert not m._sharded_across_ranks()
+
+
+def test_evaluate_accepts_a_pair_of_arrays_and_dict_outputs():
+    """`validation_data_fn=lambda: (x_val, y_val)` (the README quick start) reaches the evaluator as ONE argument; and
+    models whose outputs are dicts (BERT's heads) are evaluated with a loss over dicts."""
+    x, y = _xy(48)
+    m = _model()
+    m.fit(x, y, batch_size=16, epochs=1, verbose=0)
+    direct = m.evaluate(x, y, return_dict=True)
+    assert m.evaluate((x, y), return_dict=True) == direct
+    assert m.evaluate(lambda: (x, y), return_dict=True) == direct
+    batches = [(x[:24], y[:24]), (x[24:], y[24:])]                        # an iterable of two BATCHES stays an iterable
+    assert m.evaluate(batches, return_dict=True)["accuracy"] == pytest.approx(direct["accuracy"])
+
+    class TwoHeads(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a, self.b = torch.nn.Linear(4, 2), torch.nn.Linear(4, 3)
+
+        def forward(self, feats):
+            return {"a": self.a(feats["x"]), "b": self.b(feats["x"])}
+
+    def loss(targets, out):
+        return torch.nn.functional.cross_entropy(out["a"], targets["ya"]) + \
+            torch.nn.functional.cross_entropy(out["b"], targets["yb"])
+    d = keras.Model.from_torch(TwoHeads())
+    d.compile(loss=loss, optimizer="sgd")
+    d._device = torch.device("cpu")
+    data_ = [({"x": x[:16]}, {"ya": y[:16], "yb": y[:16]}), ({"x": x[16:32]}, {"ya": y[16:32], "yb": y[16:32]})]
+    d.fit(iter(data_ * 3), steps_per_epoch=6, epochs=1, verbose=0)
+    res = d.evaluate(iter(data_), return_dict=True)
+    assert set(res) == {"loss"} and res["loss"] > 0

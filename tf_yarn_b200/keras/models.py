@@ -446,6 +446,9 @@ class Model:
     def _infer_batches(self, x, y, batch_size, steps):
         if callable(x) and not torch.is_tensor(x):
             x = x()
+        if (y is None and isinstance(x, (tuple, list)) and len(x) == 2 and all(hasattr(t, "shape") for t in x)
+                and len(x[0]) == len(x[1])):
+            x, y = x                      # ``validation_data_fn=lambda: (x_val, y_val)``: a pair of arrays, not batches
         if hasattr(x, "shape") and not hasattr(x, "__next__"):
             return iter(_ArrayBatches(x, y, batch_size or 32, False, pin=False, drop_remainder=False)), steps
         return iter(x), steps
@@ -487,7 +490,7 @@ class Model:
                 out = self.net(xb)
                 if wd is not None:
                     wd.beat()
-                bs = out.shape[0]
+                bs = _batch_size_of(out)
                 if self._loss_fn is not None:
                     loss_sum += float(self._loss_fn(yb, out)) * bs
                 count += bs
@@ -648,6 +651,15 @@ def load_model(filepath: str, compile: bool = True) -> Model:
                       metrics=comp.get("metrics") or [])
         model._pending_engine_state = payload.get("optimizer_state")
     return model
+
+
+def _batch_size_of(out) -> int:
+    """Leading dimension of a model output (a tensor, or a dict / tuple of tensors as BERT's heads return)."""
+    if isinstance(out, dict):
+        out = next(iter(out.values()))
+    while isinstance(out, (tuple, list)):
+        out = out[0]
+    return int(out.shape[0])
 
 
 def _as_struct(t):
