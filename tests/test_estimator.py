@@ -372,3 +372,41 @@ def test_a_checkpoint_pruned_before_it_was_loaded_is_skipped_not_misreported(tmp
     last = training.continuous_eval(e, est.TrainSpec(input_fn, max_steps=6),
                                     est.EvalSpec(input_fn, steps=1, start_delay_secs=0, throttle_secs=0), timeout_secs=30)
     assert seen == [0, 4, 6] and int(last["global_step"]) == 6
+
+
+def test_logging_and_nan_hooks_take_tfs_signatures(tmp_path, caplog):
+    """tf.estimator.LoggingTensorHook(tensors, every_n_iter=...) / NanTensorHook(loss, fail_on_nan_loss=...) as user
+    code writes them; StopAtStepHook(num_steps=...) counts from the first step of THIS train() call."""
+    import torch
+    from tf_yarn_b200.estimator import feature_column as fc
+    xs = torch.randn(64, 3)
+    ys = (xs[:, 0] > 0).long()
+
+    def input_fn():
+        from tf_yarn_b200.data import Dataset
+        return Dataset.from_tensor_slices(({"x": xs}, ys)).batch(8).repeat()
+
+    def make(sub):
+        return est.LinearClassifier([fc.numeric_column("x", shape=(3,))], model_dir=str(tmp_path / sub), n_classes=2,
+                                    config=est.RunConfig(save_checkpoints_steps=None, save_checkpoints_secs=None))
+    e = make("a")
+    with caplog.at_level("INFO"):
+        e.train(input_fn, hooks=[est.LoggingTensorHook({"loss": "loss"}, every_n_iter=4, at_end=True,
+                                                       formatter=lambda v: f"L{v['step']}={v['loss']:.3f}"),
+                                 est.StopAtStepHook(num_steps=9)], max_steps=1000)
+    assert e.get_global_step() == 9
+    logged = [r.message for r in caplog.records if r.name.endswith("estimator.hooks") and r.message.startswith("L")]
+    assert [m.split("=")[0] for m in logged] == ["L4", "L8", "L9"]              # every 4 steps + at the end
+    e.train(input_fn, hooks=[est.StopAtStepHook(num_steps=3)], max_steps=1000)  # 3 MORE steps
+    assert e.get_global_step() == 12
+    assert est.LoggingTensorHook(50).every_n_iter == 50 and est.LoggingTensorHook().every_n_iter == 100
+
+    class Exploding(est.SessionRunHook):
+        def after_run(self, run_context, run_values):
+            run_context.estimator._last_loss_t = torch.tensor(float("nan"))
+
+    with pytest.raises(RuntimeError, match="NaN loss"):
+        make("b").train(input_fn, hooks=[Exploding(), est.NanTensorHook("loss")], max_steps=50)
+    soft = make("c")
+    soft.train(input_fn, hooks=[Exploding(), est.NanTensorHook("loss", fail_on_nan_loss=False)], max_steps=50)
+    assert soft.get_global_step() == 1                                          # stopped at the first NaN

@@ -12,8 +12,8 @@ from tf_yarn_b200.estimator.checkpoint import get_checkpoint_state, latest_check
 from tf_yarn_b200.estimator.config import ClusterInfo, ConfigProto, RunConfig, SessionConfig  # noqa: F401
 from tf_yarn_b200.estimator.estimator import Estimator  # noqa: F401
 from tf_yarn_b200.estimator.exporter import BestExporter, Exporter, FinalExporter, LatestExporter  # noqa: F401
-from tf_yarn_b200.estimator.hooks import (LoggingTensorHook, SessionRunArgs, SessionRunContext,  # noqa: F401
-                                          SessionRunHook, SessionRunValues, StepCounterHook, StopAtStepHook,
-                                          get_global_step)
+from tf_yarn_b200.estimator.hooks import (LoggingTensorHook, NanTensorHook, SessionRunArgs,  # noqa: F401
+                                          SessionRunContext, SessionRunHook, SessionRunValues, StepCounterHook,
+                                          StopAtStepHook, get_global_step)
 from tf_yarn_b200.estimator.spec import EstimatorSpec, EvalSpec, GraphKeys, ModeKeys, TrainSpec  # noqa: F401
 from tf_yarn_b200.estimator.training import continuous_eval, train_and_evaluate  # noqa: F401

@@ -109,15 +109,64 @@ class StepCounterHook(SessionRunHook):
 
 
 class LoggingTensorHook(SessionRunHook):
-    """Log the training loss every N steps."""
+    """``tf.estimator.LoggingTensorHook(tensors, every_n_iter=None, every_n_secs=None, at_end=False, formatter=None)``:
+    there are no graph tensors here, so the names in ``tensors`` are only echoed; what is logged is the training loss
+    (the one quantity every train step produces) every N steps / seconds."""
 
-    def __init__(self, every_n_iter: int = 100):
-        self.every_n_iter = every_n_iter
+    def __init__(self, tensors=None, every_n_iter: Optional[int] = None, every_n_secs: Optional[float] = None,
+                 at_end: bool = False, formatter=None):
+        if isinstance(tensors, int) and every_n_iter is None:        # LoggingTensorHook(100): the pre-round-2 call shape
+            tensors, every_n_iter = None, tensors
+        if every_n_iter is None and every_n_secs is None and not at_end:
+            every_n_iter = 100
+        self.tensors = list(tensors) if tensors is not None else []
+        self.every_n_iter, self.every_n_secs, self.at_end, self.formatter = every_n_iter, every_n_secs, at_end, formatter
+        self._last_time = time.time()
+        self._estimator = None
+
+    def before_run(self, run_context):
+        return SessionRunArgs(get_global_step())
+
+    def _emit(self, step, estimator) -> None:
+        loss = getattr(estimator, "_last_loss_t", None)
+        loss = float(loss) if loss is not None else estimator.last_loss
+        values = {"step": step, "loss": loss}
+        logger.info(self.formatter(values) if self.formatter else f"step = {step}, loss = {loss}")
+
+    def after_run(self, run_context, run_values):
+        step = run_values.results
+        self._estimator = run_context.estimator
+        if run_context.estimator is None:
+            return
+        due = (self.every_n_iter is not None and step % self.every_n_iter == 0) or \
+              (self.every_n_secs is not None and time.time() - self._last_time >= self.every_n_secs)
+        if due:
+            self._last_time = time.time()
+            self._emit(step, run_context.estimator)
+
+    def end(self, session=None):
+        if self.at_end and self._estimator is not None:
+            self._emit(self._estimator.get_global_step(), self._estimator)
+
+
+class NanTensorHook(SessionRunHook):
+    """``tf.estimator.NanTensorHook(loss_tensor, fail_on_nan_loss=True)``: stop (or raise) when the loss is NaN / inf.
+    Reads the loss every step (one 4-byte device-to-host copy)."""
+
+    def __init__(self, loss_tensor=None, fail_on_nan_loss: bool = True):
+        self.fail_on_nan_loss = fail_on_nan_loss
 
     def before_run(self, run_context):
         return SessionRunArgs(get_global_step())
 
     def after_run(self, run_context, run_values):
-        step = run_values.results
-        if step % self.every_n_iter == 0 and run_context.estimator is not None:
-            logger.info("step = %d, loss = %s", step, run_context.estimator.last_loss)
+        est = run_context.estimator
+        loss = getattr(est, "_last_loss_t", None) if est is not None else None
+        if loss is None:
+            return
+        value = float(loss)
+        if value != value or value in (float("inf"), float("-inf")):
+            if self.fail_on_nan_loss:
+                raise RuntimeError(f"NaN loss during training (step {run_values.results})")
+            logger.warning("NaN loss at step %s: stopping", run_values.results)
+            run_context.request_stop()
