@@ -204,3 +204,30 @@ def test_evaluate_accepts_a_pair_of_arrays_and_dict_outputs():
     d.fit(iter(data_ * 3), steps_per_epoch=6, epochs=1, verbose=0)
     res = d.evaluate(iter(data_), return_dict=True)
     assert set(res) == {"loss"} and res["loss"] > 0
+
+
+def test_validation_split_initializers_and_ignored_fit_arguments(caplog):
+    x, y = _xy(80)
+    m = _model()
+    with caplog.at_level("WARNING"):
+        h = m.fit(x, y, batch_size=16, epochs=2, verbose=0, validation_split=0.25, class_weight={0: 1.0})
+    assert "class_weight" in caplog.text                                   # not silently dropped
+    assert set(h.history) == {"loss", "accuracy", "val_loss", "val_accuracy"}
+    held_out = m.evaluate(x[60:], y[60:], return_dict=True)                # the LAST 25 % were the validation set
+    assert held_out["loss"] == pytest.approx(h.history["val_loss"][-1], rel=1e-5)
+    with pytest.raises(ValueError, match="validation_split"):
+        _model().fit(iter([(x, y)]), epochs=1, verbose=0, validation_split=0.2, steps_per_epoch=1)
+
+    torch.manual_seed(0)
+    d = keras.layers.Dense(64, input_shape=(128,), kernel_initializer="he_normal", bias_initializer="ones")
+    d.build((128,))
+    assert float(d.module.bias.detach().min()) == 1.0
+    assert abs(float(d.module.weight.detach().std()) - (2 / 128) ** 0.5) < 0.02
+    z = keras.layers.Dense(4, kernel_initializer="zeros")
+    z.build((3,))
+    assert float(z.module.weight.detach().abs().max()) == 0.0
+    c = keras.layers.Conv2D(8, 3, kernel_initializer=lambda w: torch.nn.init.constant_(w, 0.5))
+    c.build((6, 6, 2))
+    assert float(c.module.weight.detach().min()) == 0.5
+    with pytest.raises(ValueError, match="unknown initializer"):
+        keras.layers.Dense(2, kernel_initializer="orthogonal-ish").build((3,))

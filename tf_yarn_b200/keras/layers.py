@@ -43,6 +43,28 @@ def get_activation(name: Union[None, str, Callable]) -> Tuple[str, Callable]:
     return name, _ACTIVATIONS[name]
 
 
+def _init_(t: torch.Tensor, name, default: str) -> None:
+    """Keras initializer names (``kernel_initializer="he_normal"`` ...) on a torch parameter; callables get the tensor."""
+    name = default if name is None else name
+    if callable(name):
+        name(t)
+        return
+    key = str(name).lower()
+    table = {
+        "glorot_uniform": nn.init.xavier_uniform_, "xavier_uniform": nn.init.xavier_uniform_,
+        "glorot_normal": nn.init.xavier_normal_, "xavier_normal": nn.init.xavier_normal_,
+        "he_normal": lambda w: nn.init.kaiming_normal_(w, nonlinearity="relu"),
+        "he_uniform": lambda w: nn.init.kaiming_uniform_(w, nonlinearity="relu"),
+        "lecun_normal": lambda w: nn.init.kaiming_normal_(w, nonlinearity="linear"),
+        "zeros": nn.init.zeros_, "ones": nn.init.ones_,
+        "random_normal": lambda w: nn.init.normal_(w, std=0.05),
+        "random_uniform": lambda w: nn.init.uniform_(w, -0.05, 0.05),
+    }
+    if key not in table:
+        raise ValueError(f"unknown initializer {name!r}")
+    table[key](t)
+
+
 def _pair(v) -> Tuple[int, int]:
     return (v, v) if isinstance(v, int) else (int(v[0]), int(v[1]))
 
@@ -102,18 +124,20 @@ class InputLayer(Layer):
 
 
 class Dense(Layer):
-    def __init__(self, units: int, activation=None, use_bias: bool = True, **kw):
+    def __init__(self, units: int, activation=None, use_bias: bool = True, kernel_initializer=None,
+                 bias_initializer=None, **kw):
         super().__init__(**kw)
         self.units = int(units)
         self.use_bias = use_bias
         self.activation_name, self.activation = get_activation(activation)
+        self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
 
     def build_module(self, input_shape):
         lin = nn.Linear(input_shape[-1], self.units, bias=self.use_bias)
-        # Keras default: glorot_uniform kernel, zero bias
-        nn.init.xavier_uniform_(lin.weight)
+        # Keras defaults: glorot_uniform kernel, zero bias
+        _init_(lin.weight, self.kernel_initializer, "glorot_uniform")
         if lin.bias is not None:
-            nn.init.zeros_(lin.bias)
+            _init_(lin.bias, self.bias_initializer, "zeros")
         return lin
 
     def compute_output_shape(self, input_shape):
@@ -130,8 +154,9 @@ class Dense(Layer):
 
 class Conv2D(Layer):
     def __init__(self, filters: int, kernel_size, strides=(1, 1), padding: str = "valid", activation=None,
-                 use_bias: bool = True, **kw):
+                 use_bias: bool = True, kernel_initializer=None, bias_initializer=None, **kw):
         super().__init__(**kw)
+        self.kernel_initializer, self.bias_initializer = kernel_initializer, bias_initializer
         self.filters = int(filters)
         self.kernel_size = _pair(kernel_size)
         self.strides = _pair(strides)
@@ -145,9 +170,9 @@ class Conv2D(Layer):
         h, w, c = input_shape
         pad = "same" if self.padding == "same" else 0
         conv = nn.Conv2d(c, self.filters, self.kernel_size, self.strides, padding=pad, bias=self.use_bias)
-        nn.init.xavier_uniform_(conv.weight)
+        _init_(conv.weight, self.kernel_initializer, "glorot_uniform")
         if conv.bias is not None:
-            nn.init.zeros_(conv.bias)
+            _init_(conv.bias, self.bias_initializer, "zeros")
         return conv.to(memory_format=torch.channels_last)
 
     def compute_output_shape(self, input_shape):

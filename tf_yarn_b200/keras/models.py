@@ -286,13 +286,24 @@ class Model:
     def fit(self, x=None, y=None, batch_size: Optional[int] = None, epochs: int = 1, verbose: int = 1,
             callbacks: Optional[List[cb_mod.Callback]] = None, validation_data=None, shuffle: bool = True,
             steps_per_epoch: Optional[int] = None, initial_epoch: int = 0, validation_steps: Optional[int] = None,
-            **_ignored):
+            validation_split: float = 0.0, **_ignored):
         """Train.  ``x`` may be an array/tensor (with ``y`` and ``batch_size``) or an iterable of
-        ``(features, labels)`` batches such as :class:`tf_yarn_b200.data.Dataset`."""
+        ``(features, labels)`` batches such as :class:`tf_yarn_b200.data.Dataset`.  ``validation_split`` holds out
+        the LAST fraction of array inputs (before shuffling), as Keras does."""
+        if _ignored:
+            logger.warning("Model.fit: unsupported arguments ignored: %s", sorted(_ignored))
         if callable(x) and not torch.is_tensor(x):
             x = x()
         if callable(y):
             y = y()
+        if validation_split and validation_data is None:
+            if not (hasattr(x, "shape") and not hasattr(x, "__next__")) or y is None:
+                raise ValueError("validation_split needs array inputs x and y")
+            if not 0.0 < validation_split < 1.0:
+                raise ValueError("validation_split must be in (0, 1)")
+            cut = int(len(x) * (1.0 - validation_split))
+            validation_data = (x[cut:], y[cut:])
+            x, y = x[:cut], y[:cut]
         if hasattr(x, "shape") and not hasattr(x, "__next__"):
             on_gpu = (self._device or default_device()).type == "cuda"
             batches = _ArrayBatches(x, y, batch_size or 32, shuffle, pin=on_gpu, drop_remainder=on_gpu)
