@@ -209,6 +209,8 @@ class Model:
     def compile(self, optimizer="sgd", loss=None, metrics: Optional[Sequence[Any]] = None,
                 compute_dtype: Optional[torch.dtype] = None, use_cuda_graph: bool = True,
                 use_fast_path: bool = True, **_ignored) -> None:
+        if _ignored:
+            logger.warning("Model.compile: unsupported arguments ignored: %s", sorted(_ignored))
         self.optimizer = opt_mod.get(optimizer)
         self.loss = loss
         self._loss_fn = loss_mod.get(loss) if loss is not None else None
