@@ -10,7 +10,7 @@ setup(
     version="0.1.0",
     description="B200-native distributed-training launcher with the capabilities of criteo/tf-yarn",
     packages=find_packages(include=["tf_yarn_b200", "tf_yarn_b200.*"]),
-    package_data={"tf_yarn_b200": ["default.log.conf", "ops/csrc/*", "kv/*.cpp"]},
+    package_data={"tf_yarn_b200": ["default.log.conf", "ops/csrc/*", "kv/*.cpp", "examples/*.sh"]},
     python_requires=">=3.10",
     install_requires=["torch", "cloudpickle", "numpy"],
     extras_require={"tensorboard": ["tensorboard"], "parquet": ["pyarrow"], "mlflow": ["mlflow"]},
