@@ -7,9 +7,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 os.environ.setdefault("TFY_POLL_EVERY_SECS", "0.2")
+# The CPU tests work on tiny tensors: one intra-op thread is faster than eight and, above all, immune to the
+# OpenMP spin-barrier collapse on a contended / oversubscribed box (a 64-element embedding_bag took 27 ms with 8
+# threads under load).  Child processes (launcher tasks, torchrun) inherit the setting.
+if not os.path.exists("/dev/nvidia0"):          # (GPU boxes keep their threads for the fp32 reference computations)
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
 
 
 def pytest_configure(config):
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            torch.set_num_threads(1)
+    except Exception:  # noqa: BLE001
+        pass
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with `pytest -m gpu` under gpurun)")
     config.addinivalue_line("markers", "slow: multi-process integration test")
 

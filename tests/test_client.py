@@ -186,3 +186,32 @@ def test_services_carry_the_task_environment_and_scripts(monkeypatch):
     assert tb.env["TB_TERMINATION_TIMEOUT_SECONDS"] == "7" and "TB_MODEL_DIR" not in chief.env
     assert cluster.tasks == [("chief", 1, 1), ("worker", 3, 1), ("tensorboard", 1, 1)]
     assert client._default_acls_all_access() == {"enable": True, "ui_users": ["*"], "view_users": ["*"]}
+
+
+def test_one_parameter_server_plane_per_application():
+    """The peer-HBM plane needs every trainer AND ps on a GPU.  The reference's default ps_strategy_topology() labels
+    nothing: on a GPU box the trainers would otherwise pick the HBM plane while the ps serves shared memory (a hang)."""
+    from tf_yarn_b200 import topologies
+
+    def plane(specs):
+        captured = {}
+
+        class StubApp:
+            def __init__(self):
+                from tf_yarn_b200.kv import InMemoryKV
+                self.kv = InMemoryKV()
+
+        class StubClient:
+            def submit_and_connect(self, spec):
+                captured["spec"] = spec
+                return StubApp()
+        cluster = client._setup_local_cluster(specs, local_client=StubClient())
+        cluster.event_listener.stop_event.set()
+        return {k: v.env.get("TFY_PS_PLANE") for k, v in captured["spec"].services.items()}
+
+    gpu = lambda n=1: TaskSpec("1 GiB", 1, instances=n, label=NodeLabel.GPU)   # noqa: E731
+    cpu = lambda n=1: TaskSpec("1 GiB", 1, instances=n)                         # noqa: E731
+    assert set(plane(topologies.ps_strategy_topology(2, 1, "1 GiB", 1)).values()) == {"shm"}
+    assert set(plane({"chief": gpu(), "worker": gpu(2), "ps": cpu()}).values()) == {"shm"}
+    assert set(plane({"chief": gpu(), "worker": gpu(2), "ps": gpu(), "evaluator": cpu()}).values()) == {None}
+    assert set(plane({"chief": gpu(), "worker": cpu()}).values()) == {None}                    # no ps: not a PS job

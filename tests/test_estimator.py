@@ -410,3 +410,20 @@ def test_logging_and_nan_hooks_take_tfs_signatures(tmp_path, caplog):
     soft = make("c")
     soft.train(input_fn, hooks=[Exploding(), est.NanTensorHook("loss", fail_on_nan_loss=False)], max_steps=50)
     assert soft.get_global_step() == 1                                          # stopped at the first NaN
+
+
+def test_ps_role_serves_the_plane_the_application_agreed_on(monkeypatch):
+    """A ps task with a GPU still serves shared memory when the application runs the shm plane (TFY_PS_PLANE=shm)."""
+    import torch
+    from tf_yarn_b200.estimator import ps, ps_hbm, training
+    monkeypatch.setenv("TF_CONFIG", '{"cluster": {"chief": ["a:1"], "ps": ["d:4"]}, "task": {"type": "ps", "index": 0}}')
+    monkeypatch.setenv("TFY_GPU_IDS", "0")
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    served = []
+    monkeypatch.setattr(ps, "serve", lambda cluster: served.append("shm"))
+    monkeypatch.setattr(ps_hbm, "serve", lambda cluster: served.append("hbm"))
+    monkeypatch.setenv("TFY_PS_PLANE", "shm")
+    training.train_and_evaluate(None, None, None)
+    monkeypatch.delenv("TFY_PS_PLANE")
+    training.train_and_evaluate(None, None, None)
+    assert served == ["shm", "hbm", "shm"]          # (after the hbm stub returns, the code falls through to ps.serve)

@@ -100,3 +100,22 @@ def test_gpu_placement_round_robin(tmp_path, monkeypatch, n_gpu_tasks, gpus, exp
     assert [app.placement[f"worker:{i}"] for i in range(n_gpu_tasks)] == expect and app.placement["evaluator:0"] == []
     assert _wait(lambda: app.report().state == "finished")
     app.close()
+
+
+def test_cpu_labelled_tasks_do_not_see_the_gpus(tmp_path, monkeypatch):
+    """No GPU label = host CPUs only (a YARN node without GPUs): the evaluator must not compute on the chief's GPU,
+    and a CPU-labelled ps / trainer must not pick the GPU-only data plane.  TFY_CPU_TASKS_SEE_GPUS=1 restores access."""
+    monkeypatch.setenv("TFY_VISIBLE_GPUS", "0,1")
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "0,1")
+    script = 'echo "cvd=[${CUDA_VISIBLE_DEVICES-unset}] gpus=[$TFY_GPU_IDS]"'
+    spec = local.ApplicationSpec({"chief": _svc(script, label=NodeLabel.GPU), "evaluator": _svc(script)}, name="vis")
+    app = local.LocalClient(str(tmp_path / "a")).submit_and_connect(spec)
+    assert _wait(lambda: app.report().state == "finished")
+    assert "cvd=[0,1] gpus=[0]" in app.logs()["container_chief_0"]          # trainers keep every GPU visible (peer access)
+    assert "cvd=[] gpus=[]" in app.logs()["container_evaluator_0"]
+    app.close()
+    monkeypatch.setenv("TFY_CPU_TASKS_SEE_GPUS", "1")
+    app = local.LocalClient(str(tmp_path / "b")).submit_and_connect(spec)
+    assert _wait(lambda: app.report().state == "finished")
+    assert "cvd=[0,1]" in app.logs()["container_evaluator_0"]
+    app.close()

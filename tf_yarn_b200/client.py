@@ -126,6 +126,11 @@ def _setup_local_cluster(
     if cuda_runtime_hdfs_path:
         pre_script_hook = _setup_to_use_cuda_archive(env, pre_script_hook, cuda_runtime_hdfs_path)
     task_files, task_env = _setup_task_env(files, env, n_try)
+    if "ps" in task_specs and any(task_specs[t].label != topologies.NodeLabel.GPU
+                                  for t in ("chief", "worker", "ps") if t in task_specs):
+        # the peer-HBM parameter-server plane needs EVERY trainer and ps on a GPU; any CPU-labelled one (the
+        # reference's default ps_strategy_topology()) puts the whole application on the shared-memory plane
+        task_env.setdefault("TFY_PS_PLANE", "shm")
 
     services: Dict[str, ServiceSpec] = {}
     for task_type, spec in task_specs.items():

@@ -271,7 +271,7 @@ class Estimator:
         use_ps = cluster.has_ps and cluster.task_type in ("chief", "worker")
         self._restore()
         if use_ps and self._ps is None and self._network is not None:
-            if self._device.type == "cuda":
+            if self._device.type == "cuda" and os.environ.get("TFY_PS_PLANE", "auto") != "shm":
                 from tf_yarn_b200.estimator import ps_hbm
                 self._ps = ps_hbm.connect_worker(self._network, self._opt_desc, cluster, is_chief,
                                                  self._global_step, opt_by_name=self._opt_by_name)
@@ -440,7 +440,7 @@ class Estimator:
             return torch.zeros(())
         features = _to_device(features, self._device)
         labels = _to_device(labels, self._device)
-        if self._ps is not None and self._device.type == "cuda":
+        if self._ps is not None and hasattr(self._ps, "traffic_per_step"):      # the peer-HBM plane (ps_hbm)
             return self._ps_step_cuda(features, labels)
         if self._ps is not None:
             self._ps.pull(self._network)

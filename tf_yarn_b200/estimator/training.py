@@ -76,7 +76,8 @@ def train_and_evaluate(estimator, train_spec: TrainSpec, eval_spec: EvalSpec):
     role = cluster.task_type
     if cluster.distributed and role == "ps":
         import torch
-        if torch.cuda.is_available() and os.environ.get("TFY_GPU_IDS"):
+        if torch.cuda.is_available() and os.environ.get("TFY_GPU_IDS") and \
+                os.environ.get("TFY_PS_PLANE", "auto") != "shm":
             from tf_yarn_b200.estimator import ps_hbm
             ps_hbm.serve(cluster)  # never returns
         from tf_yarn_b200.estimator import ps

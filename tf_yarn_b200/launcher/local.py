@@ -208,6 +208,10 @@ class LocalApplication:
             "TFY_MEMORY_MB": str(svc.memory),
             "TFY_VCORES": str(svc.vcores),
         })
+        if svc.label != NodeLabel.GPU and os.environ.get("TFY_CPU_TASKS_SEE_GPUS", "0") != "1":
+            # a task without the GPU label runs on the host CPUs, as on a YARN node without GPUs: it must neither
+            # compute on GPU 0 next to the trainer that owns it nor pick a GPU-only data plane its peers do not use
+            env["CUDA_VISIBLE_DEVICES"] = ""
         cpus = getattr(self, "cpu_plan", {}).get(key.to_kv_str())
         argv = ["bash", "-c", svc.script]
         if cpus and shutil.which("taskset"):
