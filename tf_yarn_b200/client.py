@@ -126,6 +126,10 @@ def _setup_local_cluster(
     if cuda_runtime_hdfs_path:
         pre_script_hook = _setup_to_use_cuda_archive(env, pre_script_hook, cuda_runtime_hdfs_path)
     task_files, task_env = _setup_task_env(files, env, n_try)
+    trainer_labels = {task_specs[t].label for t in ("chief", "worker") if t in task_specs}
+    if len(trainer_labels) > 1 and "ps" not in task_specs:
+        logger.warning("chief and worker tasks carry different node labels: synchronous all-reduce training needs every "
+                       "trainer on a GPU (NVLink kernels) or every trainer on the CPU (gloo), not a mix")
     if "ps" in task_specs and any(task_specs[t].label != topologies.NodeLabel.GPU
                                   for t in ("chief", "worker", "ps") if t in task_specs):
         # the peer-HBM parameter-server plane needs EVERY trainer and ps on a GPU; any CPU-labelled one (the
