@@ -13,7 +13,7 @@ from tf_yarn_b200.metrics import Metrics
 from tf_yarn_b200.topologies import (NodeLabel, TaskSpec, allreduce_topology, ps_strategy_topology,
                                      single_server_topology)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 __all__ = ["get_safe_experiment_fn", "RunFailed", "Metrics", "TaskSpec", "NodeLabel", "single_server_topology",
            "ps_strategy_topology", "allreduce_topology"]
