@@ -1,0 +1,22 @@
+// Host build of the fused step's per-element update (ops/csrc/tfy_fused_step.cuh: tfy_step_consts + tfy_opt_update_rt),
+// so that the formulas the K4 kernel applies -- SGD-momentum / Adadelta / Adam(W) / Adagrad / FTRL, bias correction
+// from the device-resident step counter included -- can be checked against torch.optim on a CPU-only box.
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+
+static inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
+
+#include "tfy_fused_step.cuh"
+
+extern "C" void tfy_host_opt_step(int opt, TfyOptHyper* hp, int world, float* p, const float* g, float* s1, float* s2,
+                                  int n) {
+    const TfyStepConsts k = tfy_step_consts(hp, world, opt);
+    for (int i = 0; i < n; ++i) {
+        float pi = p[i], a = s1[i], b = s2[i];
+        tfy_opt_update_rt<-1>(opt, pi, g[i] * k.gscale, a, b, k.lr, k.p1, k.p2, k.eps, k.wd, k.flags, k.lr_bc1,
+                              k.bc2_rsqrt, k.first_step);
+        p[i] = pi; s1[i] = a; s2[i] = b;
+    }
+    hp->step += 1;
+}

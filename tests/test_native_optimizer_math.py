@@ -1,0 +1,79 @@
+"""The update formulas of the fused K4 kernel (ops/csrc/tfy_fused_step.cuh: tfy_step_consts + tfy_opt_update_rt), built
+for the host and checked against torch.optim on the CPU -- through the framework's own chain: mini-Keras optimizer
+-> OptimizerSpec (hyper-parameter packing) -> TfyOptHyper (device struct) -> per-element update.  The GPU tests cover
+SGD / Adadelta / Adam / Adagrad in LOCAL mode on a B200; this also covers FTRL, AdamW, Nesterov momentum, weight decay
+and the 1/world gradient scaling, on every box."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import pytest
+import torch
+
+from tf_yarn_b200 import keras
+from tf_yarn_b200.ops import native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "tf_yarn_b200", "ops", "csrc")
+CUDA_INC = "/usr/local/cuda/include"
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    cxx = shutil.which("g++")
+    if not cxx or not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA headers")
+    out = str(tmp_path_factory.mktemp("optmath") / "liboptmath.so")
+    cmd = [cxx, "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-Wl,-Bsymbolic", "-include",
+           os.path.join(ROOT, "tests", "native", "cuda_device_shim.h"), "-I", CUDA_INC, "-I", CSRC,
+           os.path.join(ROOT, "tests", "native", "optimizer_math_host.cpp"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lib = ctypes.CDLL(out)
+    lib.tfy_host_opt_step.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_int]
+    lib.tfy_host_opt_step.restype = None
+    return lib
+
+
+CASES = {
+    "sgd": keras.optimizers.SGD(0.1),
+    "sgd_momentum": keras.optimizers.SGD(0.05, momentum=0.9),
+    "sgd_nesterov_wd": keras.optimizers.SGD(0.05, momentum=0.9, nesterov=True, weight_decay=0.01),
+    "adadelta": keras.optimizers.Adadelta(1.0),
+    "adam": keras.optimizers.Adam(0.01),
+    "adam_l2": keras.optimizers.Adam(0.01, weight_decay=0.1),
+    "adamw": keras.optimizers.AdamW(0.01, weight_decay=0.1),
+    "adagrad": keras.optimizers.Adagrad(0.1),
+    "ftrl": keras.optimizers.Ftrl(0.1, l1_regularization_strength=0.002, l2_regularization_strength=0.001, beta=0.1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("world", [1, 4])
+def test_kernel_update_matches_torch_optim(lib, name, world):
+    desc = CASES[name]
+    spec = desc.to_spec()
+    n = 257
+    g = torch.Generator().manual_seed(11)
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = desc.to_torch([ref])
+    # the device-side state, initialised the way FusedShardedOptimizer does
+    p = p0.clone().contiguous()
+    s1 = torch.full((n,), spec.init_s1)
+    s2 = torch.zeros(n)
+    hyper = native.OptHyper(spec.lr, spec.p1, spec.p2, spec.eps, spec.weight_decay, 1.0, 0, spec.flags, 0, 0)
+    for step in range(7):
+        grad = torch.randn(n, generator=g) * (0.5 + 0.2 * step)
+        # the kernel receives the SUM over ranks and scales by 1/world: feed it world x the averaged gradient
+        summed = (grad * world).contiguous()
+        lib.tfy_host_opt_step(spec.code, ctypes.byref(hyper), world, p.data_ptr(), summed.data_ptr(), s1.data_ptr(),
+                              s2.data_ptr(), n)
+        ref.grad = grad.clone()
+        opt.step()
+    assert hyper.step == 7                                   # the device step counter drives Adam's bias correction
+    err = (p - ref.detach()).abs().max().item()
+    assert err < 5e-6 * max(1.0, ref.detach().abs().max().item()), (name, err)
+    if name == "ftrl":
+        assert int((p == 0).sum()) == int((ref.detach() == 0).sum())      # L1 zeroes exactly the same coordinates

@@ -55,20 +55,34 @@ __device__ __forceinline__ void tfy_bcast_pack_rt(const TfyCommCtx& c, int mode_
 // sqrtf / division sequences, i.e. 38 GB/s per SM), and the communication CTAs only have a handful of SMs: the
 // transcendental steps use the SFU approximations (MUFU.RSQ / MUFU.SQRT / MUFU.RCP, <= 2 ulp; inputs are
 // optimizer statistics, the fp32 master weights absorb the difference far below bf16 resolution).
+// (Without nvcc -- the host-side unit test of the update formulas, tests/test_native_optimizer_math.py -- the three
+// helpers are the exact functions.)
 __device__ __forceinline__ float tfy_rsqrt_approx(float x) {
+#ifdef __CUDACC__
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#else
+    return 1.f / sqrtf(x);
+#endif
 }
 __device__ __forceinline__ float tfy_sqrt_approx(float x) {
+#ifdef __CUDACC__
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#else
+    return sqrtf(x);
+#endif
 }
 __device__ __forceinline__ float tfy_div_approx(float a, float b) {
+#ifdef __CUDACC__
     float y;
     asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b));
     return y;
+#else
+    return a / b;
+#endif
 }
 
 // one element of the update; OPT_T >= 0 folds the switch at compile time, -1 dispatches on opt_rt (uniform branch)
