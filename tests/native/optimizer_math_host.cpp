@@ -20,3 +20,8 @@ extern "C" void tfy_host_opt_step(int opt, TfyOptHyper* hp, int world, float* p,
     }
     hp->step += 1;
 }
+
+// the counter-based dropout generator shared by the forward kernels and the mask-recomputing backward kernels
+extern "C" void tfy_host_uniform(uint32_t seed, uint32_t step, uint64_t idx0, float* out, int n) {
+    for (int i = 0; i < n; ++i) out[i] = tfy_uniform(seed, step, idx0 + (uint64_t)i);
+}

@@ -77,3 +77,32 @@ def test_kernel_update_matches_torch_optim(lib, name, world):
     assert err < 5e-6 * max(1.0, ref.detach().abs().max().item()), (name, err)
     if name == "ftrl":
         assert int((p == 0).sum()) == int((ref.detach() == 0).sum())      # L1 zeroes exactly the same coordinates
+
+
+def test_dropout_generator_is_uniform_stateless_and_step_dependent(lib):
+    """tfy_uniform(seed, step, index) (ops/csrc/tfy_common.cuh): the forward draws a mask, the backward kernels re-derive
+    it from the same (seed, step, index) -- so it must be a pure function -- and a replayed CUDA graph must draw a new
+    mask every step because the step is read from device memory."""
+    lib.tfy_host_uniform.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int]
+    lib.tfy_host_uniform.restype = None
+
+    def draw(seed, step, idx0, n=200_000):
+        out = torch.empty(n)
+        lib.tfy_host_uniform(seed, step, idx0, out.data_ptr(), n)
+        return out
+    u = draw(1234, 0, 0)
+    assert 0.0 <= float(u.min()) and float(u.max()) < 1.0
+    assert abs(float(u.mean()) - 0.5) < 0.005 and abs(float(u.var()) - 1 / 12) < 0.002
+    hist = torch.histc(u, bins=20, min=0, max=1) / u.numel()
+    assert float((hist - 0.05).abs().max()) < 0.003                                   # flat
+    for rate in (0.25, 0.5):
+        assert abs(float((u >= rate).float().mean()) - (1 - rate)) < 0.005           # keep probability of the kernels
+    assert torch.equal(u, draw(1234, 0, 0))                                           # pure function of its arguments
+    assert torch.equal(u[1000:2000], draw(1234, 0, 1000, 1000))                       # indexable anywhere (tiles, re-draws)
+    for other in (draw(1234, 1, 0), draw(1235, 0, 0)):                                # new step / new seed: new mask
+        assert abs(float(((u >= 0.5) == (other >= 0.5)).float().mean()) - 0.5) < 0.01
+        assert abs(float(torch.corrcoef(torch.stack([u, other]))[0, 1])) < 0.01
+    lag = torch.corrcoef(torch.stack([u[:-1], u[1:]]))[0, 1]                          # neighbours are uncorrelated
+    assert abs(float(lag)) < 0.01
+    big = draw(7, 3, (1 << 32) - 500, 1000)                                           # 64-bit indices do not wrap into repeats
+    assert not torch.equal(big[:500], big[500:])
