@@ -25,3 +25,11 @@ extern "C" void tfy_host_opt_step(int opt, TfyOptHyper* hp, int world, float* p,
 extern "C" void tfy_host_uniform(uint32_t seed, uint32_t step, uint64_t idx0, float* out, int n) {
     for (int i = 0; i < n; ++i) out[i] = tfy_uniform(seed, step, idx0 + (uint64_t)i);
 }
+
+// fp32 -> bf16 pack (round to nearest even) and back, as the fused step stores parameters and reads gradients
+extern "C" void tfy_host_bf16_roundtrip(const float* in, float* out, int n8) {
+    for (int i = 0; i < n8; ++i) {
+        const uint4 v = TfyPack<__nv_bfloat16>::pack(in + 8 * i);
+        TfyPack<__nv_bfloat16>::unpack(v, out + 8 * i);
+    }
+}

@@ -106,3 +106,18 @@ def test_dropout_generator_is_uniform_stateless_and_step_dependent(lib):
     assert abs(float(lag)) < 0.01
     big = draw(7, 3, (1 << 32) - 500, 1000)                                           # 64-bit indices do not wrap into repeats
     assert not torch.equal(big[:500], big[500:])
+
+
+def test_bf16_pack_rounds_to_nearest_even_like_torch(lib):
+    """TfyPack<bf16>::pack / unpack: the fp32 master -> bf16 parameter store of the fused step (and every bf16 epilogue)."""
+    lib.tfy_host_bf16_roundtrip.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    lib.tfy_host_bf16_roundtrip.restype = None
+    g = torch.Generator().manual_seed(5)
+    x = torch.cat([torch.randn(4096, generator=g) * 10 ** torch.randint(-6, 6, (4096,), generator=g).float(),
+                   torch.tensor([0.0, -0.0, 1.0, 1.00390625, 1.01171875, 3.3895314e38, 1e-40, -1e-40])])   # ties, huge, denormal
+    x = x[: x.numel() // 8 * 8].contiguous()
+    out = torch.empty_like(x)
+    lib.tfy_host_bf16_roundtrip(x.data_ptr(), out.data_ptr(), x.numel() // 8)
+    ref = x.bfloat16().float()
+    same = (out == ref) | (out.isnan() & ref.isnan())
+    assert bool(same.all()), (x[~same][:5], out[~same][:5], ref[~same][:5])
