@@ -15,6 +15,11 @@ fixed order every step (lock-step rounds keep the NCCL point-to-point pairing de
 waits for a straggler it would not also wait for in TF's asynchronous mode on an idle box).
 
 Launched by bench.py (plain python): re-executes itself under torch.distributed.run with one rank per cluster task.
+
+TFY_STANDIN_DEVICE=cpu runs the same protocol on host tensors over gloo (no GPU needed), e.g. the N=8 topology:
+    TFY_STANDIN_DEVICE=cpu python -m torch.distributed.run --nproc-per-node 8 bench/ps_standin.py --steps 2 \
+        --warmup 1 --trainers 6 --ps 2 --gpus 8
+(it completes there, so the rc=1 seen once at N=8 on GPUs is specific to the NCCL send/recv path).
 """
 from __future__ import annotations
 
@@ -91,13 +96,15 @@ def main():
     ap.add_argument("--gpus", type=int, required=True)
     a = ap.parse_args()
     rank, local, world = common.dist_env()
-    ngpu = torch.cuda.device_count()
-    torch.cuda.set_device(local % ngpu)
+    cpu_debug = os.environ.get("TFY_STANDIN_DEVICE") == "cpu"      # protocol debugging without GPUs (gloo, host tensors)
+    ngpu = 0 if cpu_debug else torch.cuda.device_count()
+    if not cpu_debug:
+        torch.cuda.set_device(local % ngpu)
     common.quiet_nccl()
     global _STAGE
     _STAGE = world > ngpu
     dist.init_process_group("gloo" if _STAGE else "nccl")
-    dev = torch.device("cuda")
+    dev = torch.device("cpu" if cpu_debug else "cuda")
     T, P = a.trainers, a.ps
     B, V, E, NC, NN = wd.BATCH, wd.VOCAB, wd.EMB, wd.N_CAT, wd.N_NUM
     H = list(wd.HIDDEN)
@@ -120,7 +127,7 @@ def main():
     steps, warm = a.steps, max(3, a.warmup)
     lr = 0.05
     if is_ps:
-        g = torch.Generator(device="cuda").manual_seed(7)
+        g = torch.Generator(device=dev.type).manual_seed(7)
         deep_t = {t: torch.randn(V, E, device=dev, generator=g) / E ** 0.5 for t in owned(deep_owner, ps_id)}
         deep_acc = {t: torch.full((V, E), 0.1, device=dev) for t in deep_t}
         wide_t = {t: torch.zeros(V, 1, device=dev) for t in owned(wide_owner, ps_id)}
@@ -174,7 +181,8 @@ def main():
     # ------------------------------------------------------------------------------- trainer
     from tf_yarn_b200.models import wide_deep as wdm
     batches = wdm.synthetic_batches(B, 64, V, seed=rank, n_cat=NC, n_num=NN)
-    batches = [({k: v.pin_memory() for k, v in f.items()}, y.pin_memory()) for f, y in batches]
+    if not cpu_debug:
+        batches = [({k: v.pin_memory() for k, v in f.items()}, y.pin_memory()) for f, y in batches]
     state = {"i": 0}
 
     def step(sync_loss=False):
@@ -212,7 +220,7 @@ def main():
                 deep_rows[t] = rows_d[p][k]
             for k, t in enumerate(owned(wide_owner, p)):
                 wide_rows[t] = rows_w[p][k]
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast(dev.type, dtype=torch.bfloat16):
             x = torch.cat([num] + deep_rows, dim=1)
             vi = 2
             for _ in H:
@@ -232,22 +240,29 @@ def main():
         _bcast(flag, src=0)                      # rank 0 tells the ps ranks when to stop serving
         return loss.item() if sync_loss else loss
 
+    import time
     for _ in range(warm):
         step()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(steps):
-        step()
-    e.record()
-    e.synchronize()
-    dev_ms = s.elapsed_time(e)
-    import time
+    if cpu_debug:                                        # host clock only: this mode checks the protocol, not speed
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dev_ms = (time.perf_counter() - t0) * 1e3
+    else:
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            step()
+        e.record()
+        e.synchronize()
+        dev_ms = s.elapsed_time(e)
     t0 = time.perf_counter()
     last = 0.0
     for _ in range(steps):
         last = step(sync_loss=True)
-    torch.cuda.synchronize()
+    if not cpu_debug:
+        torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     # stop the ps ranks: one more round with the flag set
     feats, y = batches[0]
