@@ -33,3 +33,16 @@ extern "C" void tfy_host_bf16_roundtrip(const float* in, float* out, int n8) {
         TfyPack<__nv_bfloat16>::unpack(v, out + 8 * i);
     }
 }
+
+// patch scheduling of the persistent convolution kernels: the (image pair, tile row, tile column) sequence of one CTA
+#include "tfy_conv_index.cuh"
+extern "C" void tfy_host_patch_walk(int tiles_x, int tiles_y, int n_cta, int block, int grid, int explicit_n_cta,
+                                    int count, int* out) {
+    blockIdx.x = (unsigned)block;
+    gridDim.x = (unsigned)grid;
+    CPatchIter it = explicit_n_cta ? CPatchIter(tiles_x, tiles_y, n_cta) : CPatchIter(tiles_x, tiles_y);
+    for (int i = 0; i < count; ++i) {
+        out[3 * i] = it.bz; out[3 * i + 1] = it.ty; out[3 * i + 2] = it.tx;
+        it.next();
+    }
+}

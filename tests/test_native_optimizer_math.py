@@ -121,3 +121,31 @@ def test_bf16_pack_rounds_to_nearest_even_like_torch(lib):
     ref = x.bfloat16().float()
     same = (out == ref) | (out.isnan() & ref.isnan())
     assert bool(same.all()), (x[~same][:5], out[~same][:5], ref[~same][:5])
+
+
+@pytest.mark.parametrize("tiles_x,tiles_y,pairs,n_cta", [(3, 3, 64, 144), (3, 3, 64, 148), (1, 1, 5, 3), (4, 2, 7, 5),
+                                                          (3, 3, 1, 148), (2, 5, 33, 37), (3, 3, 8, 8)])
+def test_persistent_conv_ctas_cover_every_patch_exactly_once(lib, tiles_x, tiles_y, pairs, n_cta):
+    """CPatchIter (ops/csrc/tfy_conv_index.cuh): CTA b of n_cta walks patches b, b + n_cta, b + 2 n_cta, ... decomposed
+    into (image pair, tile row, tile column) INCREMENTALLY (no division in the hot loop).  Over all CTAs every patch
+    of the batch must come up exactly once, in the order the division-based decomposition gives."""
+    lib.tfy_host_patch_walk.argtypes = [ctypes.c_int] * 7 + [ctypes.c_void_p]
+    lib.tfy_host_patch_walk.restype = None
+    tiles = tiles_x * tiles_y
+    n_patches = tiles * pairs
+    seen = {}
+    for explicit in (0, 1):                       # default n_cta = gridDim.x, or a grid with extra (communication) CTAs
+        seen.clear()
+        for b in range(min(n_cta, n_patches)):
+            count = (n_patches - b + n_cta - 1) // n_cta
+            out = (ctypes.c_int * (3 * count))()
+            grid = n_cta if not explicit else n_cta + 4
+            lib.tfy_host_patch_walk(tiles_x, tiles_y, n_cta, b, grid, explicit, count, out)
+            for i in range(count):
+                p = b + i * n_cta
+                want = (p // tiles, (p % tiles) // tiles_x, p % tiles_x)
+                got = (out[3 * i], out[3 * i + 1], out[3 * i + 2])
+                assert got == want, (b, i, got, want)
+                assert got not in seen
+                seen[got] = b
+        assert len(seen) == n_patches
