@@ -27,7 +27,7 @@ def lib(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("optmath") / "liboptmath.so")
     cmd = [cxx, "-O1", "-std=c++17", "-shared", "-fPIC", "-w", "-Wl,-Bsymbolic", "-include",
            os.path.join(ROOT, "tests", "native", "cuda_device_shim.h"), "-I", CUDA_INC, "-I", CSRC,
-           os.path.join(ROOT, "tests", "native", "optimizer_math_host.cpp"), "-o", out]
+           os.path.join(ROOT, "tests", "native", "device_code_host.cpp"), "-o", out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-3000:]
     lib = ctypes.CDLL(out)

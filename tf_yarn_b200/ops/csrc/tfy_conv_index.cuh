@@ -1,5 +1,5 @@
 // Patch scheduling of the persistent convolution kernels (included by tfy_conv.cu; kept in its own header so that the
-// index arithmetic can be unit-tested on the host: tests/test_native_optimizer_math.py builds it with g++).
+// index arithmetic can be unit-tested on the host: tests/test_native_device_code.py builds it with g++).
 #pragma once
 
 // Walks the patch list of a persistent CTA: p = blockIdx.x + i * gridDim.x decomposed into (image pair,

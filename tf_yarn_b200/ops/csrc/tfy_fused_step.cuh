@@ -55,7 +55,7 @@ __device__ __forceinline__ void tfy_bcast_pack_rt(const TfyCommCtx& c, int mode_
 // sqrtf / division sequences, i.e. 38 GB/s per SM), and the communication CTAs only have a handful of SMs: the
 // transcendental steps use the SFU approximations (MUFU.RSQ / MUFU.SQRT / MUFU.RCP, <= 2 ulp; inputs are
 // optimizer statistics, the fp32 master weights absorb the difference far below bf16 resolution).
-// (Without nvcc -- the host-side unit test of the update formulas, tests/test_native_optimizer_math.py -- the three
+// (Without nvcc -- the host-side unit test of the update formulas, tests/test_native_device_code.py -- the three
 // helpers are the exact functions.)
 __device__ __forceinline__ float tfy_rsqrt_approx(float x) {
 #ifdef __CUDACC__
