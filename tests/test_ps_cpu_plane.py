@@ -67,3 +67,50 @@ def test_per_variable_optimizers_and_round_robin_placement(tmp_path):
     assert shards[0].add_global_step(5) == 5 and shards[0].global_step() == 5
     for s in shards:
         s.unlink()
+
+
+def test_hbm_shard_sizing_covers_master_slots_and_row_padded_shadows():
+    """estimator/ps_hbm.py: every ps rank reserves `shard_bytes(layout)`; the fp32 area (master + optimizer slots) is
+    followed by the bf16 shadows, 2-D ones with rows padded to 8 elements (16 bytes: what a TMA tensor map needs).
+    For random layouts: regions never overlap, every shadow starts 16-byte aligned, and the reservation is enough."""
+    import random
+    from tf_yarn_b200.estimator import ps_hbm
+    rnd = random.Random(0)
+    hyper = {"lr": 0.1, "p1": 0, "p2": 0, "eps": 1e-7, "wd": 0, "init_s1": 0.1, "flags": 0}
+    for trial in range(40):
+        n_ps = rnd.choice([1, 2, 3])
+        variables, kinds = [], []
+        for i in range(rnd.randint(1, 12)):
+            if rnd.random() < 0.6:
+                shape = [rnd.randint(1, 70), rnd.choice([1, 3, 8, 13, 64, 429, 1024])]
+            else:
+                shape = [rnd.randint(1, 300)]
+            variables.append((f"v{i}", shape))
+            kinds.append(rnd.choice(["sgd", "adagrad", "adam", "ftrl"]))
+        lay = ps.Layout(variables, n_ps, "adagrad", hyper, kinds=kinds, hypers=[hyper] * len(variables))
+        conn = ps_hbm.HbmConnection.__new__(ps_hbm.HbmConnection)
+        conn.layout = lay
+        conn.ps_base = [0] * n_ps                                   # offsets relative to each rank's region
+        reserved = ps_hbm.shard_bytes(lay)
+        assert reserved % 4096 == 0
+        spans = {p: [] for p in range(n_ps)}
+        for i, (_, shape) in enumerate(variables):
+            owner = lay.owner[i]
+            for slot in range(1 + lay.var_slots[i]):
+                a = conn.master_ptr(i, slot)
+                spans[owner].append((a, a + 4 * lay.numel[i], f"v{i}/slot{slot}"))
+            s0 = conn.shadow_ptr(i)
+            ld = conn.shadow_ld(i)
+            if len(shape) == 2:
+                assert ld % 8 == 0 and ld >= shape[1] and s0 % 16 == 0
+                nbytes = 2 * shape[0] * ld
+            else:
+                assert ld == 0
+                nbytes = 2 * lay.numel[i]
+            spans[owner].append((s0, s0 + nbytes, f"v{i}/shadow"))
+        for p, regions in spans.items():
+            regions.sort()
+            for (a0, a1, na), (b0, b1, nb) in zip(regions, regions[1:]):
+                assert a1 <= b0, (trial, na, nb, a1, b0)
+            if regions:
+                assert regions[-1][1] <= reserved, (trial, regions[-1], reserved)
