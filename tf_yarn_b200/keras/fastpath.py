@@ -98,7 +98,7 @@ def build_plan(model) -> Optional[List[_Stage]]:
                 return None
             st = _Stage("conv", layer=ly, relu=ly.activation_name == "relu", pool=False, drop=0.0)
             j = i + 1
-            if j < n and isinstance(layers[j], L.MaxPooling2D):
+            if j < n and type(layers[j]) is L.MaxPooling2D:      # (AveragePooling2D SUBCLASSES it: never fuse that as max)
                 mp = layers[j]
                 h, w, _ = ly.output_shape_
                 if mp.pool_size != (2, 2) or mp.strides != (2, 2) or mp.padding != "valid" or not st.relu \
