@@ -69,3 +69,25 @@ def test_softmax_head_with_the_string_loss_and_plain_mlps():
 ])
 def test_models_outside_the_grammar_fall_back(layers, loss, metrics):
     assert _plan(layers, loss=loss, metrics=metrics) is None
+
+
+def test_kernel_envelopes_split_k_and_tensor_core_conv(monkeypatch):
+    """Which shapes go to the split-K tcgen05 GEMM and to the tcgen05 convolution kernels (everything else is served by
+    cuBLAS / cuDNN with a one-time warning)."""
+    E = fastpath.FastSequentialEngine
+    assert E._split_k(128, 128, 9216) == 24            # the MNIST Dense: 144 k-tiles, 6 per CTA
+    assert E._split_k(128, 128, 64 * 31) == 1          # K too short to be worth splitting
+    assert E._split_k(128, 128, 9217) == 1             # K not a multiple of 8 (TMA row pitch)
+    assert E._split_k(2048, 1024, 9216) == 1           # many output tiles: a plain GEMM fills the machine
+    assert 1 < E._split_k(256, 256, 4096) <= 144 // 4  # 4 tiles share the 144 CTAs
+    monkeypatch.delenv("TFY_NO_TC_CONV", raising=False)
+    m = keras_mnist_cnn()
+    m.compile(loss=LOGITS, optimizer="sgd")
+    m.build()
+    plan = fastpath.build_plan(m)
+    c1, c2 = plan[0], plan[1]
+    assert E._tc_conv(c2, 128) and E._tc_conv(c2, 2)
+    assert not E._tc_conv(c2, 3)                       # odd batch: images are processed in pairs
+    assert not E._tc_conv(c1, 128)                     # C_in = 1 has its own first-layer kernels
+    monkeypatch.setenv("TFY_NO_TC_CONV", "1")
+    assert not E._tc_conv(c2, 128)                     # A/B switch
