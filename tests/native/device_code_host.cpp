@@ -46,3 +46,32 @@ extern "C" void tfy_host_patch_walk(int tiles_x, int tiles_y, int n_cta, int blo
         it.next();
     }
 }
+
+// layout of the structs shared with Python (ctypes mirrors in tf_yarn_b200/ops/native.py)
+#include <stddef.h>
+extern "C" int tfy_host_struct_layout(int which, int* out, int cap) {
+    int n = 0;
+#define PUT(v) do { if (n < cap) out[n] = (int)(v); ++n; } while (0)
+    if (which == 0) {          // TfyCommCtx
+        PUT(sizeof(TfyCommCtx)); PUT(offsetof(TfyCommCtx, peer_base)); PUT(offsetof(TfyCommCtx, mc_base));
+        PUT(offsetof(TfyCommCtx, epoch)); PUT(offsetof(TfyCommCtx, rank)); PUT(offsetof(TfyCommCtx, world));
+        PUT(TFY_MAX_RANKS); PUT(TFY_MAX_BLOCKS); PUT(TFY_FLAGS_BYTES);
+    } else if (which == 1) {   // TfyOptHyper
+        PUT(sizeof(TfyOptHyper)); PUT(offsetof(TfyOptHyper, lr)); PUT(offsetof(TfyOptHyper, p1));
+        PUT(offsetof(TfyOptHyper, p2)); PUT(offsetof(TfyOptHyper, eps)); PUT(offsetof(TfyOptHyper, weight_decay));
+        PUT(offsetof(TfyOptHyper, grad_scale)); PUT(offsetof(TfyOptHyper, step)); PUT(offsetof(TfyOptHyper, flags));
+        PUT(offsetof(TfyOptHyper, done)); PUT(offsetof(TfyOptHyper, pad));
+    } else if (which == 2) {   // TfyOverlapStep
+        PUT(sizeof(TfyOverlapStep)); PUT(offsetof(TfyOverlapStep, c)); PUT(offsetof(TfyOverlapStep, grad_off));
+        PUT(offsetof(TfyOverlapStep, param_off)); PUT(offsetof(TfyOverlapStep, shard_n)); PUT(offsetof(TfyOverlapStep, master));
+        PUT(offsetof(TfyOverlapStep, s1)); PUT(offsetof(TfyOverlapStep, s2)); PUT(offsetof(TfyOverlapStep, hp));
+        PUT(offsetof(TfyOverlapStep, g0)); PUT(offsetof(TfyOverlapStep, g1)); PUT(offsetof(TfyOverlapStep, opt));
+        PUT(offsetof(TfyOverlapStep, mode)); PUT(offsetof(TfyOverlapStep, n_cta)); PUT(offsetof(TfyOverlapStep, slot0));
+    } else if (which == 3) {   // enums
+        PUT(TFY_BF16); PUT(TFY_F32); PUT(TFY_ALGO_ONESHOT); PUT(TFY_ALGO_TWOSHOT); PUT(TFY_ALGO_NVLS);
+        PUT(TFY_OPT_SGD); PUT(TFY_OPT_ADADELTA); PUT(TFY_OPT_ADAM); PUT(TFY_OPT_ADAGRAD); PUT(TFY_OPT_FTRL);
+        PUT(TFY_MODE_LOCAL); PUT(TFY_MODE_P2P); PUT(TFY_MODE_NVLS);
+    }
+#undef PUT
+    return n;
+}

@@ -149,3 +149,47 @@ def test_persistent_conv_ctas_cover_every_patch_exactly_once(lib, tiles_x, tiles
                 assert got not in seen
                 seen[got] = b
         assert len(seen) == n_patches
+
+
+def test_ctypes_mirrors_match_the_c_structs(lib):
+    """tf_yarn_b200/ops/native.py mirrors the structs the kernels take by value / read from device memory; a drifted
+    field would silently corrupt peer addresses or hyper-parameters.  Sizes, offsets and enum values come from the real
+    headers (sizeof / offsetof in a host build)."""
+    import re
+    from tf_yarn_b200.ops import native
+    from tf_yarn_b200.parallel import optspec
+    lib.tfy_host_struct_layout.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.tfy_host_struct_layout.restype = ctypes.c_int
+
+    def c_layout(which):
+        buf = (ctypes.c_int * 32)()
+        n = lib.tfy_host_struct_layout(which, buf, 32)
+        return list(buf[:n])
+
+    def mirror(cls):
+        return [ctypes.sizeof(cls)] + [getattr(cls, name).offset for name, _ in cls._fields_]
+
+    ctx = c_layout(0)
+    assert ctx[:6] == mirror(native.CommCtx)
+    assert ctx[6:] == [native.MAX_RANKS, native.MAX_BLOCKS, native.FLAGS_BYTES]
+    assert c_layout(1) == mirror(native.OptHyper)
+    assert c_layout(2) == mirror(native.OverlapStep)
+    assert c_layout(3) == [native.BF16, native.F32, native.ALGO_ONESHOT, native.ALGO_TWOSHOT, native.ALGO_NVLS,
+                           native.OPT_SGD, native.OPT_ADADELTA, native.OPT_ADAM, native.OPT_ADAGRAD, native.OPT_FTRL,
+                           native.MODE_LOCAL, native.MODE_P2P, native.MODE_NVLS]
+    assert (optspec.OPT_SGD, optspec.OPT_ADADELTA, optspec.OPT_ADAM, optspec.OPT_ADAGRAD, optspec.OPT_FTRL) == \
+        (native.OPT_SGD, native.OPT_ADADELTA, native.OPT_ADAM, native.OPT_ADAGRAD, native.OPT_FTRL)
+
+    # TfyPsSeg lives in a .cu file: compare field ORDER and types textually with the ctypes mirror
+    from tf_yarn_b200.estimator.ps_hbm import PsSeg
+    src = open(os.path.join(CSRC, "tfy_ps.cu")).read()
+    body = src[src.index("struct TfyPsSeg {"):]
+    body = body[: body.index("};")]
+    fields = []
+    for line in body.splitlines()[1:]:
+        line = line.split("//")[0].strip()
+        m = re.match(r"(uint64_t|int32_t|uint32_t|float)\s+([^;]+);", line)
+        if m:
+            fields += [(name.strip(), m.group(1)) for name in m.group(2).split(",")]
+    ctype_of = {"uint64_t": ctypes.c_uint64, "int32_t": ctypes.c_int32, "uint32_t": ctypes.c_uint32, "float": ctypes.c_float}
+    assert [(n, ctype_of[t]) for n, t in fields] == list(PsSeg._fields_)
