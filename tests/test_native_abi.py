@@ -6,7 +6,6 @@ import glob
 import os
 import re
 
-import pytest
 
 from tf_yarn_b200.ops import native
 
