@@ -127,3 +127,38 @@ def test_every_native_call_in_the_package_is_declared():
         assert [_py_kind(t) for t in argtypes] == c[name][1], name
     src = open(os.path.join(ROOT, "tf_yarn_b200", "keras", "engine.py")).read()
     assert 'native.declare("tfy_memcpy_async", [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p])' in src
+
+
+def test_every_kernel_launched_with_programmatic_dependent_launch_waits_for_its_dependency():
+    """A kernel launched with the programmatic-stream-serialisation attribute may start before its predecessor has
+    finished; it is only correct if it executes griddepcontrol.wait (tfy_pdl_sync / tfy_pdl_wait) before touching
+    global memory.  Every kernel passed to tfy_launch_pdl / tfy_launch_pdl_if must contain that wait, preceded only by
+    a prologue that does not dereference its global-memory arguments."""
+    launched = {}
+    sources = {}
+    for path in sorted(glob.glob(os.path.join(CSRC, "*.cu"))):
+        src = open(path).read()
+        sources[path] = src
+        for m in re.finditer(r"tfy_launch_pdl(?:_if)?\((?:[^()]*\(\)[^(]*?)*?\(\s*(tfy_\w+)", src):
+            launched.setdefault(m.group(1), path)
+    assert len(launched) >= 14, sorted(launched)
+    for kernel, path in sorted(launched.items()):
+        src = sources[path]
+        m = re.search(r"__global__[^;{]*?\b" + re.escape(kernel) + r"\s*\(", src)
+        assert m, (kernel, path)
+        body_start = src.index("{", m.end())
+        depth, i = 0, body_start
+        while True:                                             # matching brace of the kernel body
+            ch = src[i]
+            depth += ch == "{"
+            depth -= ch == "}"
+            if depth == 0:
+                break
+            i += 1
+        body = re.sub(r"//[^\n]*", "", src[body_start:i])
+        waits = [body.find(w) for w in ("tfy_pdl_sync()", "tfy_pdl_wait()") if w in body]
+        assert waits, f"{kernel} ({os.path.basename(path)}) is launched with PDL but never waits for its dependency"
+        prologue = body[:min(waits)]
+        # the prologue may set up shared memory, barriers, TMEM and prefetch tensor maps / this kernel's own state
+        for forbidden in ("tfy_ld16(", "__ldg(", "__ldcg(", "atomicAdd(", "tfy_st16(", "red_add", "cp.async.bulk.tensor"):
+            assert forbidden not in prologue, (kernel, forbidden)
