@@ -64,3 +64,30 @@ def test_shutdown_container_posts_stop_waits_and_reraises(monkeypatch):
         tf_task_common._shutdown_container(client, tasks, None, thread)
     assert b"training failed" in client.kv["worker:0/stop"]
     assert "worker:0/container_stop_time" in client.kv
+
+
+def test_allreduce_task_assigns_ranks_and_exports_the_horovod_environment(monkeypatch):
+    """Chief = rank 0, workers follow by id; every trainer turns its rank_info into the HOROVOD_* variables the
+    reference's Horovod-gloo task exports (reference: tf_yarn/tensorflow/tasks/gloo_allred_task.py:36-54,94-123)."""
+    import os
+    from fakes import FakeClient
+    from tf_yarn_b200.tensorflow.tasks import allred_task
+    from tf_yarn_b200.topologies import ContainerTask
+    tasks = [ContainerTask("worker", 2, 1), ContainerTask("chief", 0, 1), ContainerTask("worker", 0, 1),
+             ContainerTask("worker", 1, 1)]
+    client = FakeClient()
+    allred_task._driver_fn(client, tasks)
+    kv = client.kv
+    assert kv["chief:0/rank_info"] == b"0,4,0,4,0,1" and kv["worker:0/rank_info"] == b"1,4,1,4,0,1"
+    assert kv["worker:2/rank_info"] == b"3,4,3,4,0,1"
+    host, port = kv["chief:0/sock_addr"].decode().split(":")
+    assert int(port) > 0
+    monkeypatch.setenv("TFY_TASK_KEY", "worker:1")
+    for k in ("HOROVOD_RANK", "HOROVOD_SIZE", "TFY_RANK", "TFY_WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    allred_task._setup_hvd_env(client)
+    assert (os.environ["HOROVOD_RANK"], os.environ["HOROVOD_SIZE"], os.environ["HOROVOD_LOCAL_RANK"]) == ("2", "4", "2")
+    assert os.environ["HOROVOD_GLOO_RENDEZVOUS_PORT"] == port and os.environ["TFY_WORLD_SIZE"] == "4"
+    assert kv["worker:1/addr"]                                   # the reference's per-task address announcement
+    for k in [k for k in os.environ if k.startswith("HOROVOD_")] + ["TFY_RANK", "TFY_WORLD_SIZE"]:
+        monkeypatch.delenv(k, raising=False)
